@@ -1,0 +1,1005 @@
+// C-ABI of libanml_b200 (declared in include/anml_b200.h): handles, TMA
+// descriptors, kernel dispatch.  Host-side only; kernels live in the .cuh files.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/anml_b200.h"
+#include "fused_eval.cuh"
+#include "generic.cuh"
+#include "spline.cuh"
+
+using namespace anml;
+
+// ----------------------------------------------------------------------------
+// errors
+// ----------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                       \
+    do {                                                                                                   \
+        cudaError_t e__ = (expr);                                                                          \
+        if (e__ != cudaSuccess) {                                                                          \
+            const int code__ = (e__ == cudaErrorMemoryAllocation) ? ANML_ENOMEM : ANML_ECUDA;              \
+            (void)cudaGetLastError();                                                                      \
+            return fail(code__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                                  \
+    } while (0)
+
+#define TRY(expr)                 \
+    do {                          \
+        int rc__ = (expr);        \
+        if (rc__ != ANML_OK) return rc__; \
+    } while (0)
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static long long round_up_ll(long long v, long long m) { return (v + m - 1) / m * m; }
+
+// ----------------------------------------------------------------------------
+// handles
+// ----------------------------------------------------------------------------
+struct anml_design {
+    int device = 0;
+    long long n = 0;
+    int p = 0;
+    long long ld = 0;
+    double* X = nullptr;
+    bool owned = false;
+    CUtensorMap tmap;  // box 16 rows x 16 cols, 128B swizzle
+    int sm_count = 0;
+};
+
+struct PriorStore {
+    bool set = false;
+    int m = 0;
+    double *mean = nullptr, *inv_var = nullptr, *lin_mat = nullptr, *lin_mean = nullptr, *lin_inv_var = nullptr,
+           *lin_hess = nullptr;
+};
+
+struct ParamSlot {
+    const anml_design* design = nullptr;
+    int link = ANML_LINK_IDENTITY;
+    const double* offset = nullptr;  // device, borrowed
+    int off = 0;                     // first coefficient in x
+    int pad_off = 0;                 // offset of the zero-padded copy inside d_beta
+    PriorStore prior;
+};
+
+struct EventPair {
+    cudaEvent_t a, b;
+};
+
+struct anml_model {
+    int device = 0;
+    long long n = 0, n_pad = 0;
+    int family = 0, K = 0, P = 0;
+    ParamSlot par[2];
+    const double* obs = nullptr;
+    const double* se = nullptr;
+    double* obs_owned = nullptr;
+    double* se_owned = nullptr;
+    bool prior_enabled = true;
+    bool force_generic = false, no_fast = false;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    // evaluation buffers (allocated by ensure_buffers once P is known)
+    bool ready = false;
+    int beta_len = 0;
+    double *d_beta = nullptr, *h_beta = nullptr;
+    double *d_packed = nullptr, *h_packed = nullptr;
+    double *d_partials = nullptr, *d_reduced = nullptr;
+    long long partials_len = 0;
+    int* d_status = nullptr;
+    cudaEvent_t beta_copied = nullptr;  // guards reuse of h_beta across async evaluations
+    bool beta_pending = false;
+    // general-path vectors
+    double* vec[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // y0 y1 r0 r1 w00 w01 w11
+    double* d_wide = nullptr;
+    long long wide_len = 0;
+    // timing of the dominant kernel
+    std::vector<EventPair> ev_pool;
+    size_t ev_used = 0;
+    double ev_accum_ms = 0.0;
+    long long main_launches = 0, all_launches = 0;
+};
+
+// ----------------------------------------------------------------------------
+// misc
+// ----------------------------------------------------------------------------
+extern "C" const char* anml_last_error(void) { return g_err.c_str(); }
+extern "C" int anml_version(void) { return ANML_B200_VERSION; }
+
+extern "C" int anml_device_count(int* count) {
+    if (!count) return fail(ANML_EINVAL, "count is NULL");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        *count = 0;
+        return fail(ANML_ECUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    }
+    *count = c;
+    return ANML_OK;
+}
+
+extern "C" int anml_device_info(int device, int* sm_count, int64_t* total_mem, int* cc_major, int* cc_minor) {
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (total_mem) *total_mem = (int64_t)prop.totalGlobalMem;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return ANML_OK;
+}
+
+extern "C" int anml_dev_alloc(int device, int64_t bytes, void** out) {
+    if (!out || bytes < 0) return fail(ANML_EINVAL, "anml_dev_alloc: bad arguments");
+    CU_TRY(cudaSetDevice(device));
+    CU_TRY(cudaMalloc(out, bytes > 0 ? (size_t)bytes : 16));
+    return ANML_OK;
+}
+extern "C" int anml_dev_free(int device, void* dev) {
+    CU_TRY(cudaSetDevice(device));
+    CU_TRY(cudaFree(dev));
+    return ANML_OK;
+}
+extern "C" int anml_dev_upload(int device, void* dst, const void* src, int64_t bytes) {
+    CU_TRY(cudaSetDevice(device));
+    CU_TRY(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyHostToDevice));
+    return ANML_OK;
+}
+extern "C" int anml_dev_download(int device, void* dst, const void* src, int64_t bytes) {
+    CU_TRY(cudaSetDevice(device));
+    CU_TRY(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return ANML_OK;
+}
+
+// ----------------------------------------------------------------------------
+// TMA descriptor (driver entry point resolved through the runtime: no -lcuda)
+// ----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_design_tmap(anml_design* d) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CU_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres));
+        if (!sym || qres != cudaDriverEntryPointSuccess) return fail(ANML_ECUDA, "cuTensorMapEncodeTiled not available in this driver");
+        fn = (EncodeTiledFn)sym;
+    }
+    if (d->n == 0) {
+        memset(&d->tmap, 0, sizeof(d->tmap));
+        return ANML_OK;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)d->p, (cuuint64_t)d->n};
+    cuuint64_t gstride[1] = {(cuuint64_t)d->ld * sizeof(double)};
+    cuuint32_t box[2] = {16, 16};
+    cuuint32_t estride[2] = {1, 1};
+    CUresult r = fn(&d->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d->X, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ANML_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (n=%lld p=%d ld=%lld)", (int)r, d->n, d->p, d->ld);
+    return ANML_OK;
+}
+
+// ----------------------------------------------------------------------------
+// design matrix
+// ----------------------------------------------------------------------------
+static int design_finish(anml_design* d) {
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, d->device));
+    if (prop.major < 10) return fail(ANML_EUNSUPPORTED, "anml_b200 needs an sm_100 (B200) device, found sm_%d%d", prop.major, prop.minor);
+    d->sm_count = prop.multiProcessorCount;
+    return encode_design_tmap(d);
+}
+
+extern "C" int anml_design_create(int device, int64_t n_rows, int n_cols, anml_design** out) {
+    if (!out || n_rows < 0 || n_cols <= 0) return fail(ANML_EINVAL, "anml_design_create: need n_rows >= 0 and n_cols > 0");
+    if (n_rows > 2147483000LL) return fail(ANML_EUNSUPPORTED, "anml_design_create: at most 2^31 rows per device");
+    CU_TRY(cudaSetDevice(device));
+    anml_design* d = new (std::nothrow) anml_design();
+    if (!d) return fail(ANML_ENOMEM, "out of host memory");
+    d->device = device;
+    d->n = n_rows;
+    d->p = n_cols;
+    d->ld = round_up(n_cols, 2);
+    d->owned = true;
+    const size_t bytes = (size_t)(n_rows > 0 ? n_rows : 1) * d->ld * sizeof(double);
+    cudaError_t e = cudaMalloc(&d->X, bytes);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        delete d;
+        return fail(ANML_ENOMEM, "cudaMalloc of %zu bytes for the design matrix failed: %s", bytes, cudaGetErrorString(e));
+    }
+    e = cudaMemset(d->X, 0, bytes);
+    if (e != cudaSuccess) {
+        cudaFree(d->X);
+        delete d;
+        return fail(ANML_ECUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+    }
+    int rc = design_finish(d);
+    if (rc != ANML_OK) {
+        cudaFree(d->X);
+        delete d;
+        return rc;
+    }
+    *out = d;
+    return ANML_OK;
+}
+
+extern "C" int anml_design_wrap_device(int device, int64_t n_rows, int n_cols, double* dev, int64_t ld, anml_design** out) {
+    if (!out || !dev || n_rows < 0 || n_cols <= 0 || ld < n_cols) return fail(ANML_EINVAL, "anml_design_wrap_device: bad shape");
+    if ((ld & 1) || (reinterpret_cast<uintptr_t>(dev) & 15)) return fail(ANML_EINVAL, "anml_design_wrap_device: ld must be even and the pointer 16-byte aligned (TMA row stride)");
+    if (n_rows > 2147483000LL) return fail(ANML_EUNSUPPORTED, "anml_design_wrap_device: at most 2^31 rows per device");
+    CU_TRY(cudaSetDevice(device));
+    anml_design* d = new (std::nothrow) anml_design();
+    if (!d) return fail(ANML_ENOMEM, "out of host memory");
+    d->device = device;
+    d->n = n_rows;
+    d->p = n_cols;
+    d->ld = ld;
+    d->X = dev;
+    d->owned = false;
+    int rc = design_finish(d);
+    if (rc != ANML_OK) {
+        delete d;
+        return rc;
+    }
+    *out = d;
+    return ANML_OK;
+}
+
+extern "C" int anml_design_destroy(anml_design* d) {
+    if (!d) return ANML_OK;
+    cudaSetDevice(d->device);
+    if (d->owned && d->X) cudaFree(d->X);
+    delete d;
+    return ANML_OK;
+}
+
+extern "C" int anml_design_shape(const anml_design* d, int64_t* n_rows, int* n_cols, int64_t* ld, double** dev) {
+    if (!d) return fail(ANML_EINVAL, "design is NULL");
+    if (n_rows) *n_rows = d->n;
+    if (n_cols) *n_cols = d->p;
+    if (ld) *ld = d->ld;
+    if (dev) *dev = d->X;
+    return ANML_OK;
+}
+
+static int grid_for(long long work, int threads, int sm_count, int per_sm = 8) {
+    long long blocks = (work + threads - 1) / threads;
+    long long cap = (long long)sm_count * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+extern "C" int anml_design_set_columns(anml_design* d, int col0, int ncols, const double* src, int64_t src_ld, int src_on_device) {
+    if (!d || !src) return fail(ANML_EINVAL, "anml_design_set_columns: NULL argument");
+    if (col0 < 0 || ncols <= 0 || col0 + ncols > d->p || src_ld < ncols) return fail(ANML_EINVAL, "anml_design_set_columns: columns [%d, %d) outside the %d-column design or src_ld too small", col0, col0 + ncols, d->p);
+    if (d->n == 0) return ANML_OK;
+    CU_TRY(cudaSetDevice(d->device));
+    if (src_on_device) {
+        scatter_columns_kernel<<<grid_for(d->n * ncols, 256, d->sm_count), 256>>>(d->X, d->n, d->ld, col0, ncols, src, src_ld);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaDeviceSynchronize());
+        return ANML_OK;
+    }
+    // host source: stage through a bounded dense device buffer, chunk of rows at a time
+    const long long max_elems = 1LL << 25;  // 256 MiB of doubles
+    long long rows_per_chunk = max_elems / ncols;
+    if (rows_per_chunk < 1) rows_per_chunk = 1;
+    if (rows_per_chunk > d->n) rows_per_chunk = d->n;
+    double* tmp = nullptr;
+    CU_TRY(cudaMalloc(&tmp, (size_t)rows_per_chunk * ncols * sizeof(double)));
+    for (long long r0 = 0; r0 < d->n; r0 += rows_per_chunk) {
+        const long long rows = (d->n - r0 < rows_per_chunk) ? d->n - r0 : rows_per_chunk;
+        cudaError_t e = cudaMemcpy2D(tmp, (size_t)ncols * sizeof(double), src + r0 * src_ld, (size_t)src_ld * sizeof(double),
+                                     (size_t)ncols * sizeof(double), (size_t)rows, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            scatter_columns_kernel<<<grid_for(rows * ncols, 256, d->sm_count), 256>>>(d->X + r0 * d->ld, rows, d->ld, col0, ncols, tmp, ncols);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            cudaFree(tmp);
+            (void)cudaGetLastError();
+            return fail(ANML_ECUDA, "anml_design_set_columns: %s", cudaGetErrorString(e));
+        }
+    }
+    CU_TRY(cudaFree(tmp));
+    return ANML_OK;
+}
+
+static int run_spline(int device, int sm_count, const double* x_dev, long long n, const double* knots, int nk, int degree,
+                      int ldegree, int rdegree, int order, double* out_dev, long long ld, int col0, int32_t* idx_dev) {
+    if (nk < 2 || nk > SPLINE_MAX_KNOTS) return fail(ANML_EINVAL, "spline needs between 2 and %d knots, got %d", SPLINE_MAX_KNOTS, nk);
+    if (degree < 0 || degree > SPLINE_MAX_DEGREE) return fail(ANML_EUNSUPPORTED, "spline degree must be in [0, %d], got %d", SPLINE_MAX_DEGREE, degree);
+    if (order < 0) return fail(ANML_EINVAL, "spline derivative order must be non-negative");
+    for (int i = 1; i < nk; ++i)
+        if (!(knots[i] >= knots[i - 1])) return fail(ANML_EINVAL, "spline knots must be sorted ascending");
+    if (!(knots[nk - 1] > knots[0])) return fail(ANML_EINVAL, "spline knots must span a non-empty interval");
+    if (ldegree < 0) ldegree = 0;
+    if (rdegree < 0) rdegree = 0;
+    if (ldegree > degree) ldegree = degree;
+    if (rdegree > degree) rdegree = degree;
+    const int nt = nk + 2 * degree;
+    std::vector<double> t(nt);
+    for (int i = 0; i < degree; ++i) t[i] = knots[0];
+    for (int i = 0; i < nk; ++i) t[degree + i] = knots[i];
+    for (int i = 0; i < degree; ++i) t[degree + nk + i] = knots[nk - 1];
+    double* t_dev = nullptr;
+    CU_TRY(cudaMalloc(&t_dev, nt * sizeof(double)));
+    cudaError_t e = cudaMemcpy(t_dev, t.data(), nt * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n > 0) {
+        SplineArgs a;
+        a.x = x_dev; a.n = n; a.t = t_dev; a.nk = nk; a.degree = degree; a.ldegree = ldegree; a.rdegree = rdegree;
+        a.order = order; a.out = out_dev; a.ld = ld; a.col0 = col0; a.idx_out = idx_dev;
+        spline_design_kernel<<<grid_for(n, 256, sm_count), 256, nt * sizeof(double)>>>(a);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    }
+    cudaFree(t_dev);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(ANML_ECUDA, "spline_design_kernel: %s", cudaGetErrorString(e));
+    }
+    (void)device;
+    return ANML_OK;
+}
+
+extern "C" int anml_design_set_spline(anml_design* d, int col0, const double* x, int x_on_device, const double* knots, int n_knots,
+                                      int degree, int ldegree, int rdegree, int order, int32_t* interval_out) {
+    if (!d || !x || !knots) return fail(ANML_EINVAL, "anml_design_set_spline: NULL argument");
+    const int nb = n_knots - 1 + degree;
+    if (col0 < 0 || col0 + nb > d->p) return fail(ANML_EINVAL, "anml_design_set_spline: %d basis columns at %d do not fit a %d-column design", nb, col0, d->p);
+    CU_TRY(cudaSetDevice(d->device));
+    double* x_tmp = nullptr;
+    int32_t* idx_dev = nullptr;
+    const size_t nn = (size_t)(d->n > 0 ? d->n : 1);
+    if (!x_on_device) {
+        CU_TRY(cudaMalloc(&x_tmp, nn * sizeof(double)));
+        cudaError_t e = cudaMemcpy(x_tmp, x, (size_t)d->n * sizeof(double), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(x_tmp);
+            return fail(ANML_ECUDA, "upload of spline abscissae failed: %s", cudaGetErrorString(e));
+        }
+    }
+    if (interval_out) {
+        cudaError_t e = cudaMalloc(&idx_dev, nn * sizeof(int32_t));
+        if (e != cudaSuccess) {
+            if (x_tmp) cudaFree(x_tmp);
+            (void)cudaGetLastError();
+            return fail(ANML_ENOMEM, "cudaMalloc for interval indices failed");
+        }
+    }
+    int rc = run_spline(d->device, d->sm_count, x_on_device ? x : x_tmp, d->n, knots, n_knots, degree, ldegree, rdegree, order,
+                        d->X, d->ld, col0, idx_dev);
+    if (rc == ANML_OK && interval_out && d->n > 0) {
+        cudaError_t e = cudaMemcpy(interval_out, idx_dev, (size_t)d->n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(ANML_ECUDA, "download of interval indices failed: %s", cudaGetErrorString(e));
+    }
+    if (x_tmp) cudaFree(x_tmp);
+    if (idx_dev) cudaFree(idx_dev);
+    return rc;
+}
+
+extern "C" int anml_design_download(const anml_design* d, double* host_out, int64_t out_ld) {
+    if (!d || !host_out || out_ld < d->p) return fail(ANML_EINVAL, "anml_design_download: bad arguments");
+    if (d->n == 0) return ANML_OK;
+    CU_TRY(cudaSetDevice(d->device));
+    CU_TRY(cudaMemcpy2D(host_out, (size_t)out_ld * sizeof(double), d->X, (size_t)d->ld * sizeof(double), (size_t)d->p * sizeof(double),
+                        (size_t)d->n, cudaMemcpyDeviceToHost));
+    return ANML_OK;
+}
+
+extern "C" int anml_spline_design(int device, const double* x_host, int64_t n, const double* knots, int n_knots, int degree,
+                                  int ldegree, int rdegree, int order, double* out_host, int32_t* interval_out) {
+    if (!x_host || !knots || !out_host || n < 0) return fail(ANML_EINVAL, "anml_spline_design: bad arguments");
+    const int nb = n_knots - 1 + degree;
+    if (nb <= 0) return fail(ANML_EINVAL, "anml_spline_design: no basis functions");
+    anml_design* d = nullptr;
+    TRY(anml_design_create(device, n, nb, &d));
+    int rc = anml_design_set_spline(d, 0, x_host, 0, knots, n_knots, degree, ldegree, rdegree, order, interval_out);
+    if (rc == ANML_OK) rc = anml_design_download(d, out_host, nb);
+    anml_design_destroy(d);
+    return rc;
+}
+
+// y (optionally through the link at `order`) for all rows
+static int launch_linpred(const anml_design* d, const double* beta_dev, const double* offset, int link, int order, double* out,
+                          int* status, cudaStream_t st) {
+    if (d->n == 0) return ANML_OK;
+    const int npairs = (int)(d->ld / 2);
+    int gs = 1;
+    while (gs < npairs && gs < 32) gs <<= 1;
+    const int threads = 256;
+    const long long rows_per_block = (threads / 32) * (32 / gs);
+    const int grid = grid_for(d->n * (threads / rows_per_block), threads, d->sm_count, 8);
+    const size_t smem = (size_t)d->ld * sizeof(double);
+    if (smem > 48 * 1024) return fail(ANML_EUNSUPPORTED, "design wider than 6144 columns is not supported");
+#define LP(GS) linpred_kernel<GS><<<grid, threads, smem, st>>>(d->X, d->n, d->p, d->ld, beta_dev, offset, link, order, out, status)
+    switch (gs) {
+        case 1: LP(1); break;
+        case 2: LP(2); break;
+        case 4: LP(4); break;
+        case 8: LP(8); break;
+        case 16: LP(16); break;
+        default: LP(32); break;
+    }
+#undef LP
+    CU_TRY(cudaGetLastError());
+    return ANML_OK;
+}
+
+extern "C" int anml_design_params(const anml_design* d, const double* beta_host, const double* offset_dev, int link, int order,
+                                  double* out_host) {
+    if (!d || !beta_host || !out_host) return fail(ANML_EINVAL, "anml_design_params: NULL argument");
+    if (order < 0 || order > 2) return fail(ANML_EINVAL, "Order must be 0, 1 or 2.");
+    if (link < 0 || link > 4) return fail(ANML_EINVAL, "unknown link %d", link);
+    if (d->n == 0) return ANML_OK;
+    CU_TRY(cudaSetDevice(d->device));
+    const long long n = d->n;
+    const int p = d->p;
+    long long out_elems = n;
+    if (order == 1) out_elems = n * p;
+    if (order == 2) out_elems = n * p * (long long)p;
+    size_t free_b = 0, total_b = 0;
+    CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+    if ((double)out_elems * 8.0 + (double)n * 8.0 > 0.9 * (double)free_b)
+        return fail(ANML_ENOMEM, "get_params(order=%d) would materialise %.3g GB on the device; use the model evaluation instead", order, out_elems * 8.0 / 1e9);
+    double *beta_dev = nullptr, *z = nullptr, *out = nullptr;
+    int* status = nullptr;
+    int rc = ANML_OK;
+    cudaError_t e = cudaMalloc(&beta_dev, (size_t)p * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&z, (size_t)n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&status, sizeof(int));
+    if (e == cudaSuccess && order > 0) e = cudaMalloc(&out, (size_t)out_elems * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemset(status, 0, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(beta_dev, beta_host, (size_t)p * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rc = launch_linpred(d, beta_dev, offset_dev, link, order, z, status, 0);
+        if (rc == ANML_OK && order == 1) jacobian_kernel<<<grid_for(out_elems, 256, d->sm_count), 256>>>(d->X, n, p, d->ld, z, out);
+        if (rc == ANML_OK && order == 2) tensor2_kernel<<<grid_for(out_elems, 256, d->sm_count), 256>>>(d->X, n, p, d->ld, z, out);
+        if (rc == ANML_OK) e = cudaGetLastError();
+        if (rc == ANML_OK && e == cudaSuccess) e = cudaMemcpy(out_host, order == 0 ? z : out, (size_t)out_elems * sizeof(double), cudaMemcpyDeviceToHost);
+        int flag = 0;
+        if (rc == ANML_OK && e == cudaSuccess) e = cudaMemcpy(&flag, status, sizeof(int), cudaMemcpyDeviceToHost);
+        if (rc == ANML_OK && e == cudaSuccess && flag) {
+            rc = fail(ANML_EDOMAIN, link == ANML_LINK_LOG ? "All values for log function must be positive."
+                                                          : "All values for logit function must be strictly between 0 and 1.");
+        }
+    }
+    if (beta_dev) cudaFree(beta_dev);
+    if (z) cudaFree(z);
+    if (out) cudaFree(out);
+    if (status) cudaFree(status);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? ANML_ENOMEM : ANML_ECUDA, "anml_design_params: %s", cudaGetErrorString(e));
+    }
+    return rc;
+}
+
+// ----------------------------------------------------------------------------
+// model
+// ----------------------------------------------------------------------------
+extern "C" int anml_model_create(int device, int64_t n_rows, int family, int n_params, anml_model** out) {
+    if (!out || n_rows < 0) return fail(ANML_EINVAL, "anml_model_create: bad arguments");
+    if (family < 0 || family > 3) return fail(ANML_EINVAL, "unknown family %d", family);
+    const int need = (family == ANML_FAMILY_GAUSSIAN_MEANVAR) ? 2 : 1;
+    if (n_params != need) return fail(ANML_EINVAL, "family %d takes %d parameter(s), got %d", family, need, n_params);
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(ANML_EUNSUPPORTED, "anml_b200 needs an sm_100 (B200) device, found sm_%d%d", prop.major, prop.minor);
+    anml_model* m = new (std::nothrow) anml_model();
+    if (!m) return fail(ANML_ENOMEM, "out of host memory");
+    m->device = device;
+    m->n = n_rows;
+    m->n_pad = round_up_ll(n_rows > 0 ? n_rows : 1, 32);
+    m->family = family;
+    m->K = n_params;
+    m->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete m;
+        return fail(ANML_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    }
+    *out = m;
+    return ANML_OK;
+}
+
+static void free_prior(PriorStore& s) {
+    double** ptrs[] = {&s.mean, &s.inv_var, &s.lin_mat, &s.lin_mean, &s.lin_inv_var, &s.lin_hess};
+    for (double** p : ptrs) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
+    s.set = false;
+    s.m = 0;
+}
+
+static void free_eval_buffers(anml_model* m) {
+    if (m->d_beta) cudaFree(m->d_beta);
+    if (m->h_beta) cudaFreeHost(m->h_beta);
+    if (m->d_packed) cudaFree(m->d_packed);
+    if (m->h_packed) cudaFreeHost(m->h_packed);
+    if (m->d_partials) cudaFree(m->d_partials);
+    if (m->d_reduced) cudaFree(m->d_reduced);
+    if (m->d_status) cudaFree(m->d_status);
+    if (m->d_wide) cudaFree(m->d_wide);
+    for (double*& v : m->vec) {
+        if (v) cudaFree(v);
+        v = nullptr;
+    }
+    m->d_beta = m->h_beta = m->d_packed = m->h_packed = m->d_partials = m->d_reduced = m->d_wide = nullptr;
+    m->d_status = nullptr;
+    m->wide_len = 0;
+    m->ready = false;
+}
+
+extern "C" int anml_model_destroy(anml_model* m) {
+    if (!m) return ANML_OK;
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    free_eval_buffers(m);
+    for (int k = 0; k < 2; ++k) free_prior(m->par[k].prior);
+    if (m->obs_owned) cudaFree(m->obs_owned);
+    if (m->se_owned) cudaFree(m->se_owned);
+    for (EventPair& ep : m->ev_pool) {
+        cudaEventDestroy(ep.a);
+        cudaEventDestroy(ep.b);
+    }
+    if (m->beta_copied) cudaEventDestroy(m->beta_copied);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+    return ANML_OK;
+}
+
+extern "C" int anml_model_set_param(anml_model* m, int k, const anml_design* design, int link, const double* offset_dev) {
+    if (!m || !design) return fail(ANML_EINVAL, "anml_model_set_param: NULL argument");
+    if (k < 0 || k >= m->K) return fail(ANML_EINVAL, "parameter index %d out of range (model has %d)", k, m->K);
+    if (link < 0 || link > 4) return fail(ANML_EINVAL, "unknown link %d", link);
+    if (design->n != m->n) return fail(ANML_EINVAL, "design has %lld rows, model has %lld", design->n, m->n);
+    if (design->device != m->device) return fail(ANML_EINVAL, "design lives on device %d, model on %d", design->device, m->device);
+    CU_TRY(cudaSetDevice(m->device));
+    if (m->stream) CU_TRY(cudaStreamSynchronize(m->stream));
+    if (m->par[k].design && m->par[k].design->p != design->p) {
+        free_prior(m->par[k].prior);
+        free_eval_buffers(m);
+    }
+    m->par[k].design = design;
+    m->par[k].link = link;
+    m->par[k].offset = offset_dev;
+    return ANML_OK;
+}
+
+static int set_row_vector(anml_model* m, const double* src, int on_device, const double** view, double** owned) {
+    CU_TRY(cudaSetDevice(m->device));
+    if (m->stream) CU_TRY(cudaStreamSynchronize(m->stream));
+    if (*owned) {
+        CU_TRY(cudaFree(*owned));
+        *owned = nullptr;
+    }
+    *view = nullptr;
+    if (!src) return ANML_OK;
+    if (on_device) {
+        *view = src;  // borrowed
+        return ANML_OK;
+    }
+    CU_TRY(cudaMalloc(owned, (size_t)m->n_pad * sizeof(double)));
+    CU_TRY(cudaMemset(*owned, 0, (size_t)m->n_pad * sizeof(double)));
+    if (m->n > 0) CU_TRY(cudaMemcpy(*owned, src, (size_t)m->n * sizeof(double), cudaMemcpyHostToDevice));
+    *view = *owned;
+    return ANML_OK;
+}
+
+extern "C" int anml_model_set_obs(anml_model* m, const double* obs, int on_device) {
+    if (!m || !obs) return fail(ANML_EINVAL, "anml_model_set_obs: NULL argument");
+    return set_row_vector(m, obs, on_device, &m->obs, &m->obs_owned);
+}
+
+extern "C" int anml_model_set_obs_se(anml_model* m, const double* se, int on_device) {
+    if (!m) return fail(ANML_EINVAL, "anml_model_set_obs_se: NULL model");
+    return set_row_vector(m, se, on_device, &m->se, &m->se_owned);
+}
+
+static int upload_vec(double** dst, const std::vector<double>& v) {
+    CU_TRY(cudaMalloc(dst, (v.size() ? v.size() : 1) * sizeof(double)));
+    if (!v.empty()) CU_TRY(cudaMemcpy(*dst, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return ANML_OK;
+}
+
+extern "C" int anml_model_set_gaussian_prior(anml_model* m, int k, const double* mean, const double* sd, int n_lin,
+                                             const double* lin_mat, const double* lin_mean, const double* lin_sd) {
+    if (!m) return fail(ANML_EINVAL, "anml_model_set_gaussian_prior: NULL model");
+    if (k < 0 || k >= m->K || !m->par[k].design) return fail(ANML_ESTATE, "set the design of parameter %d before its prior", k);
+    if (n_lin < 0 || (n_lin > 0 && (!lin_mat || !lin_mean || !lin_sd))) return fail(ANML_EINVAL, "linear prior arrays missing");
+    CU_TRY(cudaSetDevice(m->device));
+    if (m->stream) CU_TRY(cudaStreamSynchronize(m->stream));
+    const int p = m->par[k].design->p;
+    PriorStore& s = m->par[k].prior;
+    free_prior(s);
+    std::vector<double> mu(p, 0.0), iv(p, 0.0);
+    for (int j = 0; j < p; ++j) {
+        if (mean) mu[j] = mean[j];
+        if (sd) {
+            if (!(sd[j] > 0.0)) return fail(ANML_EINVAL, "Gaussian prior standard deviations must be positive.");
+            iv[j] = std::isinf(sd[j]) ? 0.0 : 1.0 / (sd[j] * sd[j]);
+        }
+    }
+    std::vector<double> lmean(n_lin), liv(n_lin), lh((size_t)(n_lin > 0 ? p * p : 0), 0.0), lmat((size_t)n_lin * p);
+    for (int i = 0; i < n_lin; ++i) {
+        if (!(lin_sd[i] > 0.0)) return fail(ANML_EINVAL, "Gaussian prior standard deviations must be positive.");
+        lmean[i] = lin_mean[i];
+        liv[i] = std::isinf(lin_sd[i]) ? 0.0 : 1.0 / (lin_sd[i] * lin_sd[i]);
+        for (int j = 0; j < p; ++j) lmat[(size_t)i * p + j] = lin_mat[(size_t)i * p + j];
+    }
+    // (M^T / sd^2) M is constant in x: GaussianPrior.hessian, prior/main.py:197
+    for (int i = 0; i < n_lin; ++i)
+        for (int a = 0; a < p; ++a) {
+            const double ma = lmat[(size_t)i * p + a] * liv[i];
+            if (ma == 0.0) continue;
+            for (int b = 0; b <= a; ++b) lh[(size_t)a * p + b] += ma * lmat[(size_t)i * p + b];
+        }
+    for (int a = 0; a < p && n_lin > 0; ++a)  // mirror the lower triangle: exactly symmetric
+        for (int b = 0; b < a; ++b) lh[(size_t)b * p + a] = lh[(size_t)a * p + b];
+    TRY(upload_vec(&s.mean, mu));
+    TRY(upload_vec(&s.inv_var, iv));
+    TRY(upload_vec(&s.lin_mat, lmat));
+    TRY(upload_vec(&s.lin_mean, lmean));
+    TRY(upload_vec(&s.lin_inv_var, liv));
+    TRY(upload_vec(&s.lin_hess, lh));
+    s.m = n_lin;
+    s.set = true;
+    return ANML_OK;
+}
+
+extern "C" int anml_model_set_prior_enabled(anml_model* m, int enabled) {
+    if (!m) return fail(ANML_EINVAL, "NULL model");
+    m->prior_enabled = enabled != 0;
+    return ANML_OK;
+}
+
+extern "C" int anml_model_set_option(anml_model* m, const char* name, int64_t value) {
+    if (!m || !name) return fail(ANML_EINVAL, "NULL argument");
+    if (!strcmp(name, "force_generic")) m->force_generic = value != 0;
+    else if (!strcmp(name, "no_fast_math_paths")) m->no_fast = value != 0;
+    else return fail(ANML_EINVAL, "unknown option '%s'", name);
+    return ANML_OK;
+}
+
+extern "C" int anml_model_num_coefs(const anml_model* m, int* total) {
+    if (!m || !total) return fail(ANML_EINVAL, "NULL argument");
+    int P = 0;
+    for (int k = 0; k < m->K; ++k) {
+        if (!m->par[k].design) return fail(ANML_ESTATE, "parameter %d has no design matrix", k);
+        P += m->par[k].design->p;
+    }
+    *total = P;
+    return ANML_OK;
+}
+
+static int fused_el(int nb16, bool hess) {
+    const int nb8 = 2 * nb16, nt = nb8 * (nb8 + 1) / 2;
+    return ((hess ? 2 * nt : 0) + nb8 + 1) * 32;
+}
+
+static int ensure_buffers(anml_model* m) {
+    if (m->ready) return ANML_OK;
+    int P = 0;
+    TRY(anml_model_num_coefs(m, &P));
+    if (!m->obs) return fail(ANML_ESTATE, "observations not set");
+    m->P = P;
+    int at = 0, pad_at = P;
+    for (int k = 0; k < m->K; ++k) {
+        m->par[k].off = at;
+        m->par[k].pad_off = pad_at;
+        at += m->par[k].design->p;
+        pad_at += round_up(m->par[k].design->p, 64);
+    }
+    m->beta_len = pad_at;
+    const size_t packed = (size_t)2 + P + (size_t)P * P;
+    CU_TRY(cudaMalloc(&m->d_beta, m->beta_len * sizeof(double)));
+    CU_TRY(cudaMallocHost(&m->h_beta, m->beta_len * sizeof(double)));
+    CU_TRY(cudaMalloc(&m->d_packed, packed * sizeof(double)));
+    CU_TRY(cudaMallocHost(&m->h_packed, packed * sizeof(double)));
+    CU_TRY(cudaMemset(m->d_packed, 0, packed * sizeof(double)));
+    int max_ld = 0;
+    for (int k = 0; k < m->K; ++k) max_ld = max_ld > (int)m->par[k].design->ld ? max_ld : (int)m->par[k].design->ld;
+    long long plen = (long long)m->sm_count * fused_el(4, true);
+    const long long xtr_len = (long long)m->sm_count * 4 * max_ld;
+    if (xtr_len > plen) plen = xtr_len;
+    if ((long long)m->sm_count * 8 > plen) plen = (long long)m->sm_count * 8;
+    m->partials_len = plen;
+    CU_TRY(cudaMalloc(&m->d_partials, (size_t)plen * sizeof(double)));
+    CU_TRY(cudaMalloc(&m->d_reduced, (size_t)fused_el(4, true) * sizeof(double)));
+    CU_TRY(cudaMalloc(&m->d_status, sizeof(int)));
+    if (!m->beta_copied) CU_TRY(cudaEventCreateWithFlags(&m->beta_copied, cudaEventDisableTiming));
+    m->ready = true;
+    return ANML_OK;
+}
+
+static int ensure_vec(anml_model* m, int which) {
+    if (m->vec[which]) return ANML_OK;
+    CU_TRY(cudaMalloc(&m->vec[which], (size_t)m->n_pad * sizeof(double)));
+    CU_TRY(cudaMemset(m->vec[which], 0, (size_t)m->n_pad * sizeof(double)));
+    return ANML_OK;
+}
+
+static EventPair* next_events(anml_model* m) {
+    if (m->ev_used == m->ev_pool.size()) {
+        if (m->ev_pool.size() >= 4096) return nullptr;  // bounded; beyond that launches go untimed
+        EventPair ep;
+        if (cudaEventCreate(&ep.a) != cudaSuccess) return nullptr;
+        if (cudaEventCreate(&ep.b) != cudaSuccess) {
+            cudaEventDestroy(ep.a);
+            return nullptr;
+        }
+        m->ev_pool.push_back(ep);
+    }
+    return &m->ev_pool[m->ev_used++];
+}
+
+template <int NB16, bool HESS, int MODE>
+static int launch_fused_t(const anml_design* d, const FusedArgs& a, int grid, cudaStream_t st) {
+    using C = FusedCfg<NB16>;
+    static bool configured = false;
+    auto kern = fused_eval_kernel<NB16, HESS, MODE>;
+    if (!configured) {
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        configured = true;
+    }
+    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(d->tmap, a);
+    CU_TRY(cudaGetLastError());
+    return ANML_OK;
+}
+
+// fused kernel + partial reduction + layout undo for one parameter block
+static int run_fused_block(anml_model* m, const anml_design* d, FusedArgs a, bool hess, int mode, int row_off, int col_off,
+                           bool write_grad, bool add_obj, bool timed, cudaStream_t st) {
+    const int nb16 = (d->p + 15) / 16;
+    if (nb16 > 4) return fail(ANML_EUNSUPPORTED, "fused path handles at most 64 columns");
+    const long long nblk = (d->n + 31) / 32;
+    int grid = (int)((nblk + 7) / 8);
+    if (grid > m->sm_count) grid = m->sm_count;
+    if (grid < 1) grid = 1;
+    a.partials = m->d_partials;
+    a.status = m->d_status;
+    EventPair* ep = timed ? next_events(m) : nullptr;
+    if (ep) CU_TRY(cudaEventRecord(ep->a, st));
+    int rc = ANML_OK;
+#define FUSED_CASE(NB)                                                                         \
+    case NB:                                                                                   \
+        if (mode == 0) rc = hess ? launch_fused_t<NB, true, 0>(d, a, grid, st) : launch_fused_t<NB, false, 0>(d, a, grid, st); \
+        else rc = hess ? launch_fused_t<NB, true, 1>(d, a, grid, st) : launch_fused_t<NB, false, 1>(d, a, grid, st);           \
+        break;
+    switch (nb16) {
+        FUSED_CASE(1)
+        FUSED_CASE(2)
+        FUSED_CASE(3)
+        FUSED_CASE(4)
+    }
+#undef FUSED_CASE
+    TRY(rc);
+    if (ep) CU_TRY(cudaEventRecord(ep->b, st));
+    const int el = fused_el(nb16, hess);
+    reduce_partials_kernel<<<(el + 255) / 256, 256, 0, st>>>(m->d_partials, grid, el, m->d_reduced);
+    CU_TRY(cudaGetLastError());
+    assemble_kernel<<<1, 256, 0, st>>>(m->d_reduced, nb16, hess ? 1 : 0, d->p, m->d_packed, m->P, row_off, col_off,
+                                       write_grad ? 1 : 0, add_obj ? 1 : 0);
+    CU_TRY(cudaGetLastError());
+    m->main_launches += 1;
+    m->all_launches += 3;
+    return ANML_OK;
+}
+
+static int run_priors(anml_model* m, int want, cudaStream_t st) {
+    if (!m->prior_enabled) return ANML_OK;
+    for (int k = 0; k < m->K; ++k) {
+        const PriorStore& s = m->par[k].prior;
+        if (!s.set) continue;
+        PriorArgs a;
+        a.p = m->par[k].design->p; a.off = m->par[k].off; a.P_total = m->P; a.m = s.m; a.want = want;
+        a.beta = m->d_beta; a.mean = s.mean; a.inv_var = s.inv_var; a.lin_mat = s.lin_mat; a.lin_mean = s.lin_mean;
+        a.lin_inv_var = s.lin_inv_var; a.lin_hess = s.lin_hess; a.packed = m->d_packed;
+        const size_t smem = (size_t)(s.m > 0 ? s.m : 1) * sizeof(double);
+        if (smem > 48 * 1024) return fail(ANML_EUNSUPPORTED, "more than 6144 linear prior rows on one parameter");
+        add_priors_kernel<<<1, 256, smem, st>>>(a);
+        CU_TRY(cudaGetLastError());
+        m->all_launches += 1;
+    }
+    return ANML_OK;
+}
+
+static int eval_general(anml_model* m, int want, cudaStream_t st);
+
+// H block (row_off, col_off) = Xa^T diag(w) Xb for designs wider than 64 columns
+// or two different designs.
+static int run_wide_hessian(anml_model* m, const anml_design* da, const anml_design* db, const double* w, int row_off, int col_off,
+                            cudaStream_t st) {
+    (void)m; (void)da; (void)db; (void)w; (void)row_off; (void)col_off; (void)st;
+    return fail(ANML_EUNSUPPORTED, "Hessian blocks wider than 64 columns are not implemented yet");
+}
+
+static int eval_on_stream(anml_model* m, const double* x_host, int want, cudaStream_t st) {
+    TRY(ensure_buffers(m));
+    for (int k = 0; k < m->K; ++k)
+        if (m->par[k].design->n != m->n) return fail(ANML_ESTATE, "design of parameter %d changed shape", k);
+    const bool hess = (want & ANML_WANT_HESS) != 0;
+    // stage beta: [x (P) | zero-padded copy per parameter]
+    if (m->beta_pending) {
+        CU_TRY(cudaEventSynchronize(m->beta_copied));
+        m->beta_pending = false;
+    }
+    memset(m->h_beta, 0, m->beta_len * sizeof(double));
+    memcpy(m->h_beta, x_host, m->P * sizeof(double));
+    for (int k = 0; k < m->K; ++k) memcpy(m->h_beta + m->par[k].pad_off, x_host + m->par[k].off, m->par[k].design->p * sizeof(double));
+    CU_TRY(cudaMemcpyAsync(m->d_beta, m->h_beta, m->beta_len * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaEventRecord(m->beta_copied, st));
+    m->beta_pending = true;
+    CU_TRY(cudaMemsetAsync(m->d_status, 0, sizeof(int), st));
+
+    const anml_design* d0 = m->par[0].design;
+    if (m->K == 1 && d0->p <= 64 && !m->force_generic) {
+        FusedArgs a;
+        a.n = m->n; a.p = d0->p; a.link = m->par[0].link; a.family = m->family; a.fast = m->no_fast ? 0 : 1;
+        a.beta = m->d_beta + m->par[0].pad_off; a.obs = m->obs; a.se = m->se; a.offset = m->par[0].offset;
+        a.rvec = nullptr; a.wvec = nullptr; a.partials = nullptr; a.status = nullptr;
+        TRY(run_fused_block(m, d0, a, hess, 0, 0, 0, true, false, true, st));
+    } else {
+        TRY(eval_general(m, want, st));
+    }
+    TRY(run_priors(m, want, st));
+    set_flag_kernel<<<1, 1, 0, st>>>(m->d_packed + 1 + m->P + (size_t)m->P * m->P, m->d_status);
+    CU_TRY(cudaGetLastError());
+    m->all_launches += 1;
+    return ANML_OK;
+}
+
+// General path: any K <= 2, any width.  linear predictors -> row terms ->
+// per-block gradient / Hessian kernels.
+static int eval_general(anml_model* m, int want, cudaStream_t st) {
+    const bool hess = (want & ANML_WANT_HESS) != 0;
+    const int K = m->K;
+    for (int k = 0; k < K; ++k) {
+        TRY(ensure_vec(m, k));      // y_k
+        TRY(ensure_vec(m, 2 + k));  // r_k
+    }
+    TRY(ensure_vec(m, 4));
+    if (K == 2) {
+        TRY(ensure_vec(m, 5));
+        TRY(ensure_vec(m, 6));
+    }
+    for (int k = 0; k < K; ++k) {
+        TRY(launch_linpred(m->par[k].design, m->d_beta + m->par[k].off, m->par[k].offset, 0, -1, m->vec[k], m->d_status, st));
+        m->all_launches += 1;
+    }
+    RowTermsArgs ra;
+    ra.n = m->n; ra.family = m->family; ra.nparams = K; ra.link0 = m->par[0].link; ra.link1 = (K == 2) ? m->par[1].link : 0;
+    ra.fast = m->no_fast ? 0 : 1;
+    ra.y0 = m->vec[0]; ra.y1 = m->vec[1]; ra.obs = m->obs; ra.se = m->se;
+    ra.r0 = m->vec[2]; ra.r1 = m->vec[3]; ra.w00 = m->vec[4]; ra.w01 = m->vec[5]; ra.w11 = m->vec[6];
+    ra.obj_partials = m->d_partials; ra.status = m->d_status;
+    const int rgrid = grid_for(m->n, 256, m->sm_count, 8);
+    rowterms_kernel<<<rgrid, 256, 0, st>>>(ra);
+    CU_TRY(cudaGetLastError());
+    sum_partials_kernel<<<1, 256, 0, st>>>(m->d_partials, rgrid, m->d_packed, 0);
+    CU_TRY(cudaGetLastError());
+    m->all_launches += 2;
+
+    for (int k = 0; k < K; ++k) {
+        const anml_design* d = m->par[k].design;
+        const double* wkk = (k == 0) ? m->vec[4] : m->vec[6];
+        if (d->p <= 64) {
+            FusedArgs a;
+            memset(&a, 0, sizeof(a));
+            a.n = m->n; a.p = d->p; a.rvec = m->vec[2 + k]; a.wvec = wkk;
+            TRY(run_fused_block(m, d, a, hess, 1, m->par[k].off, m->par[k].off, true, true, true, st));
+        } else {
+            // gradient: streaming X^T r
+            const int warps = 4;
+            int grid = m->sm_count;
+            if ((long long)grid * warps > d->n) grid = (int)((d->n + warps - 1) / warps);
+            if (grid < 1) grid = 1;
+            const size_t smem = (size_t)warps * d->ld * sizeof(double);
+            if (smem > 48 * 1024) return fail(ANML_EUNSUPPORTED, "design wider than 1536 columns is not supported by the gradient kernel");
+            xtr_kernel<<<grid, warps * 32, smem, st>>>(d->X, d->n, d->ld, m->vec[2 + k], m->d_partials);
+            CU_TRY(cudaGetLastError());
+            column_sum_kernel<<<(d->p + 255) / 256, 256, 0, st>>>(m->d_partials, grid, d->ld, d->p, m->d_packed + 1 + m->par[k].off);
+            CU_TRY(cudaGetLastError());
+            m->all_launches += 2;
+            if (hess) TRY(run_wide_hessian(m, d, d, wkk, m->par[k].off, m->par[k].off, st));
+        }
+    }
+    if (K == 2 && hess) {
+        const anml_design* da = m->par[0].design;
+        const anml_design* db = m->par[1].design;
+        if (da == db && da->p <= 64) {
+            FusedArgs a;
+            memset(&a, 0, sizeof(a));
+            a.n = m->n; a.p = da->p; a.rvec = m->vec[5]; a.wvec = m->vec[5];
+            TRY(run_fused_block(m, da, a, true, 1, m->par[0].off, m->par[1].off, false, true, true, st));
+        } else {
+            TRY(run_wide_hessian(m, da, db, m->vec[5], m->par[0].off, m->par[1].off, st));
+        }
+    }
+    return ANML_OK;
+}
+
+extern "C" int anml_model_eval_async(anml_model* m, const double* x_host, int want, double* packed_dev, void* stream) {
+    if (!m || !x_host) return fail(ANML_EINVAL, "anml_model_eval_async: NULL argument");
+    CU_TRY(cudaSetDevice(m->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
+    TRY(eval_on_stream(m, x_host, want, st));
+    if (packed_dev && packed_dev != m->d_packed) {
+        const size_t packed = (size_t)2 + m->P + (size_t)m->P * m->P;
+        CU_TRY(cudaMemcpyAsync(packed_dev, m->d_packed, packed * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    return ANML_OK;
+}
+
+extern "C" int anml_model_eval(anml_model* m, const double* x_host, int want, double* obj, double* grad, double* hess) {
+    if (!m || !x_host) return fail(ANML_EINVAL, "anml_model_eval: NULL argument");
+    if (((want & ANML_WANT_OBJ) && !obj) || ((want & ANML_WANT_GRAD) && !grad) || ((want & ANML_WANT_HESS) && !hess))
+        return fail(ANML_EINVAL, "anml_model_eval: output buffer missing for a requested quantity");
+    CU_TRY(cudaSetDevice(m->device));
+    // the gradient is always produced (it rides on the same pass); the Hessian only on request
+    TRY(eval_on_stream(m, x_host, want | ANML_WANT_OBJ | ANML_WANT_GRAD, m->stream));
+    const size_t P = m->P;
+    const size_t flag_at = 1 + P + P * P;
+    if (want & ANML_WANT_HESS) {
+        CU_TRY(cudaMemcpyAsync(m->h_packed, m->d_packed, (flag_at + 1) * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    } else {
+        CU_TRY(cudaMemcpyAsync(m->h_packed, m->d_packed, (1 + P) * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+        CU_TRY(cudaMemcpyAsync(m->h_packed + flag_at, m->d_packed + flag_at, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    }
+    CU_TRY(cudaStreamSynchronize(m->stream));
+    if (m->h_packed[flag_at] != 0.0) return fail(ANML_EDOMAIN, "linear predictor outside the domain of a Log/Logit mapping");
+    if (want & ANML_WANT_OBJ) *obj = m->h_packed[0];
+    if (want & ANML_WANT_GRAD) memcpy(grad, m->h_packed + 1, P * sizeof(double));
+    if (want & ANML_WANT_HESS) memcpy(hess, m->h_packed + 1 + P, P * P * sizeof(double));
+    return ANML_OK;
+}
+
+extern "C" int anml_model_kernel_time(anml_model* m, int reset, double* total_ms, int64_t* launches, int64_t* all_launches) {
+    if (!m) return fail(ANML_EINVAL, "NULL model");
+    CU_TRY(cudaSetDevice(m->device));
+    for (size_t i = 0; i < m->ev_used; ++i) {
+        CU_TRY(cudaEventSynchronize(m->ev_pool[i].b));
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, m->ev_pool[i].a, m->ev_pool[i].b));
+        m->ev_accum_ms += ms;
+    }
+    m->ev_used = 0;
+    if (total_ms) *total_ms = m->ev_accum_ms;
+    if (launches) *launches = m->main_launches;
+    if (all_launches) *all_launches = m->all_launches;
+    if (reset) {
+        m->ev_accum_ms = 0.0;
+        m->main_launches = 0;
+        m->all_launches = 0;
+    }
+    return ANML_OK;
+}

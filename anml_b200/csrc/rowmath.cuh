@@ -1,0 +1,150 @@
+// Per-row scalar math: SmoothMapping values/derivatives and the family NLL terms.
+#pragma once
+#include "common.cuh"
+
+namespace anml {
+
+enum Link : int { LINK_IDENTITY = 0, LINK_EXP = 1, LINK_LOG = 2, LINK_EXPIT = 3, LINK_LOGIT = 4 };
+enum Family : int { FAM_GAUSSIAN = 0, FAM_BINOMIAL = 1, FAM_POISSON = 2, FAM_GAUSSIAN_MEANVAR = 3 };
+
+struct LinkVal {
+    double f, d1, d2;  // f(y), f'(y), f''(y)
+    bool ok;           // y inside the mapping's domain
+};
+
+// anml's SmoothMapping family, src/anml/parameter/smoothmapping.py.
+// expit keeps the reference's exp(-y) formulation (:121-126) so overflow
+// behaviour (nan at order >= 1 for y < -709.78) is the same.
+__device__ __forceinline__ LinkVal link_eval(int link, double y) {
+    LinkVal v;
+    v.ok = true;
+    switch (link) {
+        case LINK_EXP: {  // :76-78
+            const double e = exp(y);
+            v.f = e; v.d1 = e; v.d2 = e;
+            break;
+        }
+        case LINK_LOG: {  // :96-104, domain :98-99
+            v.ok = (y > 0.0);
+            const double inv = 1.0 / y;
+            v.f = log(y); v.d1 = inv; v.d2 = -inv * inv;
+            break;
+        }
+        case LINK_EXPIT: {  // :119-126
+            const double z = exp(-y);
+            const double q = 1.0 / (1.0 + z);
+            v.f = q; v.d1 = z * q * q; v.d2 = z * (z - 1.0) * q * q * q;
+            break;
+        }
+        case LINK_LOGIT: {  // :146-156, domain :148-151
+            v.ok = (y > 0.0) && (y < 1.0);
+            const double s = y * (1.0 - y);
+            const double inv = 1.0 / s;
+            v.f = log(y / (1.0 - y)); v.d1 = inv; v.d2 = (2.0 * y - 1.0) * inv * inv;
+            break;
+        }
+        default:  // identity :59-65
+            v.f = y; v.d1 = 1.0; v.d2 = 0.0;
+            break;
+    }
+    return v;
+}
+
+// Value of one order only (Parameter.get_params hands transform(y, order) on).
+__device__ __forceinline__ double link_order(int link, double y, int order, bool& ok) {
+    const LinkVal v = link_eval(link, y);
+    ok = v.ok;
+    return order == 0 ? v.f : (order == 1 ? v.d1 : v.d2);
+}
+
+// Per-row terms of a one-parameter family, already chained through the link:
+//   l = NLL term, r = dl/dtheta * f', w = d2l/dtheta2 * f'^2 + dl/dtheta * f''
+// so that grad = X^T r and Hessian = X^T diag(w) X  (SURVEY.md 3.3).
+struct RowTerms1 {
+    double l, r, w;
+    bool ok;
+};
+
+__device__ __forceinline__ RowTerms1 row_terms1(int family, int link, bool fast, double y, double obs, double se) {
+    RowTerms1 o;
+    o.ok = true;
+    if (fast && family == FAM_BINOMIAL && link == LINK_EXPIT) {
+        // canonical logistic: one exp, one log, one reciprocal per row
+        const double z = exp(-y);
+        const double q = 1.0 / (1.0 + z);
+        o.l = log1p(z) + (1.0 - obs) * y;
+        o.r = q - obs;
+        o.w = z * q * q;
+        return o;
+    }
+    if (fast && family == FAM_GAUSSIAN && link == LINK_IDENTITY) {
+        const double iv = 1.0 / (se * se);
+        const double res = y - obs;
+        o.r = res * iv;
+        o.w = iv;
+        o.l = 0.5 * res * o.r;
+        return o;
+    }
+    if (fast && family == FAM_POISSON && link == LINK_EXP) {
+        const double lam = exp(y);
+        o.l = lam - obs * y;
+        o.r = lam - obs;
+        o.w = lam;
+        return o;
+    }
+    const LinkVal f = link_eval(link, y);
+    o.ok = f.ok;
+    double l, d1, d2;
+    const double th = f.f;
+    if (family == FAM_BINOMIAL) {
+        const double om = 1.0 - th;
+        l = -(obs * log(th) + (1.0 - obs) * log(om));
+        d1 = -obs / th + (1.0 - obs) / om;
+        d2 = obs / (th * th) + (1.0 - obs) / (om * om);
+    } else if (family == FAM_POISSON) {
+        l = th - obs * log(th);
+        d1 = 1.0 - obs / th;
+        d2 = obs / (th * th);
+    } else {  // gaussian, fixed se
+        const double iv = 1.0 / (se * se);
+        const double res = obs - th;
+        l = 0.5 * res * res * iv;
+        d1 = -res * iv;
+        d2 = iv;
+    }
+    o.l = l;
+    o.r = d1 * f.d1;
+    o.w = d2 * f.d1 * f.d1 + d1 * f.d2;
+    return o;
+}
+
+// Two-parameter Gaussian (mean mu = f0(y0), variance v = f1(y1)):
+//   l = 1/2 log v + 1/2 (obs-mu)^2 / v
+struct RowTerms2 {
+    double l, r0, r1, w00, w01, w11;
+    bool ok;
+};
+
+__device__ __forceinline__ RowTerms2 row_terms2(int link0, int link1, double y0, double y1, double obs) {
+    RowTerms2 o;
+    const LinkVal f0 = link_eval(link0, y0);
+    const LinkVal f1 = link_eval(link1, y1);
+    o.ok = f0.ok && f1.ok;
+    const double mu = f0.f, v = f1.f;
+    const double iv = 1.0 / v;
+    const double res = obs - mu;
+    const double d0 = -res * iv;
+    const double d1 = 0.5 * iv - 0.5 * res * res * iv * iv;
+    const double h00 = iv;
+    const double h01 = res * iv * iv;
+    const double h11 = -0.5 * iv * iv + res * res * iv * iv * iv;
+    o.l = 0.5 * log(v) + 0.5 * res * res * iv;
+    o.r0 = d0 * f0.d1;
+    o.r1 = d1 * f1.d1;
+    o.w00 = h00 * f0.d1 * f0.d1 + d0 * f0.d2;
+    o.w01 = h01 * f0.d1 * f1.d1;
+    o.w11 = h11 * f1.d1 * f1.d1 + d1 * f1.d2;
+    return o;
+}
+
+}  // namespace anml

@@ -1,0 +1,119 @@
+"""GPU parity of the evaluation kernels against the NumPy oracle, through the
+C-ABI (ctypes).  Tolerances are BASELINE.json's: objective / gradient 1e-10,
+Hessian 1e-9, relative (gradient and Hessian relative to their largest entry)."""
+import numpy as np
+import pytest
+
+from oracle import anml_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LINK_NAME = {"identity": "Identity", "exp": "Exp", "log": "Log", "expit": "Expit", "logit": "Logit"}
+
+
+def make_problem(family, n, p, seed, link=None, with_offset=False, with_se=False):
+    rng = np.random.default_rng(seed)
+    X = rng.normal(size=(n, p))
+    if p > 0:
+        X[:, 0] = 1.0
+    beta_true = rng.normal(size=p) * 0.1
+    y = X @ beta_true
+    off = rng.normal(size=n) * 0.2 if with_offset else None
+    if off is not None:
+        y = y + off
+    se = rng.uniform(0.5, 1.5, size=n) if with_se else None
+    if family == "gaussian":
+        link = link or "identity"
+        obs = O.link_eval(link, y) + 0.1 * rng.normal(size=n)
+    elif family == "binomial":
+        link = link or "expit"
+        obs = (rng.uniform(size=n) < 1 / (1 + np.exp(-y))).astype(float)
+    else:
+        link = link or "exp"
+        obs = rng.poisson(np.exp(y)).astype(float)
+    return X, obs, se, off, link, 0.5 * beta_true
+
+
+def gpu_eval(family, X, obs, se, off, link, x, prior=None, options=()):
+    from anml_b200 import _native as N
+
+    n, p = X.shape
+    design = N.Design(n, p)
+    design.set_columns(0, X)
+    off_buf = N.DeviceBuffer(0, off) if off is not None else None
+    model = N.NativeModel(n, family, 1)
+    model.set_param(0, design, N.LINK_CODES[LINK_NAME[link]], off_buf)
+    model.set_obs(obs)
+    if se is not None:
+        model.set_obs_se(se)
+    if prior is not None:
+        model.set_gaussian_prior(0, *prior)
+    for name, val in options:
+        model.set_option(name, val)
+    out = model.eval(x)
+    out2 = model.eval(x)  # determinism: bitwise identical on repeat
+    assert out[0] == out2[0] and np.array_equal(out[1], out2[1]) and np.array_equal(out[2], out2[2])
+    return out
+
+
+def check(got, want, og=1e-10, h=1e-9):
+    o, g, H = got
+    ow, gw, Hw = want
+    assert abs(o - ow) <= og * abs(ow)
+    assert np.abs(g - gw).max() <= og * max(np.abs(gw).max(), 1e-300)
+    assert np.abs(H - Hw).max() <= h * np.abs(Hw).max()
+    assert np.array_equal(H, H.T)
+
+
+@pytest.mark.parametrize("p", [1, 4, 16, 17, 22, 33, 48, 63, 64])
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 20011])
+def test_binomial_expit_shapes(n, p):
+    X, obs, se, off, link, x = make_problem("binomial", n, p, seed=n * 100 + p)
+    want = O.model_eval_fused("binomial", obs, [X], [link], x)
+    check(gpu_eval("binomial", X, obs, se, off, link, x), want)
+
+
+@pytest.mark.parametrize("family,link", [("gaussian", "identity"), ("gaussian", "exp"), ("binomial", "expit"),
+                                         ("poisson", "exp"), ("gaussian", "expit")])
+@pytest.mark.parametrize("fast", [0, 1])
+def test_families_links_offset_se(family, link, fast):
+    X, obs, se, off, link, x = make_problem(family, 5003, 7, seed=7, link=link, with_offset=True, with_se=(family == "gaussian"))
+    want = O.model_eval_fused(family, obs, [X], [link], x, offsets=[off], obs_se=se)
+    got = gpu_eval(family, X, obs, se, off, link, x, options=(("no_fast_math_paths", 1 - fast),))
+    check(got, want)
+
+
+def test_general_path_matches_fused():
+    X, obs, se, off, link, x = make_problem("binomial", 4099, 37, seed=3, with_offset=True)
+    want = O.model_eval_fused("binomial", obs, [X], [link], x, offsets=[off])
+    got = gpu_eval("binomial", X, obs, se, off, link, x, options=(("force_generic", 1),))
+    check(got, want)
+
+
+def test_priors_direct_and_linear():
+    X, obs, se, off, link, x = make_problem("binomial", 3000, 6, seed=5)
+    rng = np.random.default_rng(1)
+    mean, sd = rng.normal(size=6) * 0.1, np.array([1.0, 0.5, np.inf, 2.0, 1.0, 3.0])
+    M, lm, ls = rng.normal(size=(9, 6)), rng.normal(size=9), rng.uniform(0.5, 2.0, size=9)
+    want = O.model_eval_fused("binomial", obs, [X], [link], x, priors=[{"direct": (mean, sd), "linear": (lm, ls, M)}])
+    check(gpu_eval("binomial", X, obs, se, off, link, x, prior=(mean, sd, M, lm, ls)), want)
+
+
+def test_golden_model_cases(golden):
+    for case, fam in [("gauss_p4", "gaussian"), ("binom_p6", "binomial"), ("binom_p64", "binomial"),
+                      ("poisson_p5_off", "poisson"), ("gauss_exp_p3", "gaussian")]:
+        X = golden[f"model/{case}/X"]
+        link = str(golden[f"model/{case}/links"])
+        key = f"model/{case}/offset"
+        off = golden[key] if key in golden.files else None
+        sd = float(golden[f"model/{case}/prior_sd"])
+        p = X.shape[1]
+        prior = (np.zeros(p), np.full(p, sd)) if sd > 0 else None
+        got = gpu_eval(fam, X, golden[f"model/{case}/obs"], golden[f"model/{case}/se"], off, link, golden[f"model/{case}/x"], prior=prior)
+        check(got, (float(golden[f"model/{case}/obj"]), golden[f"model/{case}/grad"], golden[f"model/{case}/hess"]))
+
+
+def test_log_link_domain_error():
+    X, obs, se, off, link, x = make_problem("gaussian", 100, 3, seed=2)
+    with pytest.raises(ValueError):
+        gpu_eval("gaussian", X, np.abs(obs) + 1, se, off, "log", -np.abs(x) - 1.0)
