@@ -14,6 +14,7 @@
 
 #include "../../include/anml_b200.h"
 #include "fused_eval.cuh"
+#include "fused_hess.cuh"
 #include "generic.cuh"
 #include "spline.cuh"
 
@@ -63,7 +64,8 @@ struct anml_design {
     long long ld = 0;
     double* X = nullptr;
     bool owned = false;
-    CUtensorMap tmap;  // box 16 rows x 16 cols, 128B swizzle
+    CUtensorMap tmap;    // box 16 rows x 16 cols, 128B swizzle
+    CUtensorMap tmap32;  // box 32 rows x 16 cols, 128B swizzle
     int sm_count = 0;
 };
 
@@ -97,7 +99,7 @@ struct anml_model {
     double* obs_owned = nullptr;
     double* se_owned = nullptr;
     bool prior_enabled = true;
-    bool force_generic = false, no_fast = false;
+    bool force_generic = false, no_fast = false, no_specialise = false;
     cudaStream_t stream = nullptr;
     int sm_count = 0;
     // evaluation buffers (allocated by ensure_buffers once P is known)
@@ -188,10 +190,9 @@ static int encode_design_tmap(anml_design* d) {
         if (!sym || qres != cudaDriverEntryPointSuccess) return fail(ANML_ECUDA, "cuTensorMapEncodeTiled not available in this driver");
         fn = (EncodeTiledFn)sym;
     }
-    if (d->n == 0) {
-        memset(&d->tmap, 0, sizeof(d->tmap));
-        return ANML_OK;
-    }
+    memset(&d->tmap, 0, sizeof(d->tmap));
+    memset(&d->tmap32, 0, sizeof(d->tmap32));
+    if (d->n == 0) return ANML_OK;
     cuuint64_t gdim[2] = {(cuuint64_t)d->p, (cuuint64_t)d->n};
     cuuint64_t gstride[1] = {(cuuint64_t)d->ld * sizeof(double)};
     cuuint32_t box[2] = {16, 16};
@@ -199,6 +200,10 @@ static int encode_design_tmap(anml_design* d) {
     CUresult r = fn(&d->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d->X, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ANML_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (n=%lld p=%d ld=%lld)", (int)r, d->n, d->p, d->ld);
+    cuuint32_t box32[2] = {16, 32};
+    r = fn(&d->tmap32, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d->X, gdim, gstride, box32, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ANML_ECUDA, "cuTensorMapEncodeTiled (32-row box) failed with CUresult %d", (int)r);
     return ANML_OK;
 }
 
@@ -686,6 +691,7 @@ extern "C" int anml_model_set_option(anml_model* m, const char* name, int64_t va
     if (!m || !name) return fail(ANML_EINVAL, "NULL argument");
     if (!strcmp(name, "force_generic")) m->force_generic = value != 0;
     else if (!strcmp(name, "no_fast_math_paths")) m->no_fast = value != 0;
+    else if (!strcmp(name, "no_warp_specialisation")) m->no_specialise = value != 0;
     else return fail(ANML_EINVAL, "unknown option '%s'", name);
     return ANML_OK;
 }
@@ -776,13 +782,28 @@ static int launch_fused_t(const anml_design* d, const FusedArgs& a, int grid, cu
     return ANML_OK;
 }
 
+template <int NB16>
+static int launch_hess_t(const anml_design* d, const FusedArgs& a, int grid, cudaStream_t st) {
+    using C = HessCfg<NB16>;
+    static bool configured = false;
+    auto kern = fused_hess_kernel<NB16>;
+    if (!configured) {
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        configured = true;
+    }
+    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(d->tmap32, a);
+    CU_TRY(cudaGetLastError());
+    return ANML_OK;
+}
+
 // fused kernel + partial reduction + layout undo for one parameter block
 static int run_fused_block(anml_model* m, const anml_design* d, FusedArgs a, bool hess, int mode, int row_off, int col_off,
                            bool write_grad, bool add_obj, bool timed, cudaStream_t st) {
     const int nb16 = (d->p + 15) / 16;
     if (nb16 > 4) return fail(ANML_EUNSUPPORTED, "fused path handles at most 64 columns");
     const long long nblk = (d->n + 31) / 32;
-    int grid = (int)((nblk + 7) / 8);
+    const bool specialised = (mode == 0) && hess && !m->no_specialise;
+    int grid = (int)((nblk + (specialised ? 3 : 7)) / (specialised ? 4 : 8));
     if (grid > m->sm_count) grid = m->sm_count;
     if (grid < 1) grid = 1;
     a.partials = m->d_partials;
@@ -795,6 +816,14 @@ static int run_fused_block(anml_model* m, const anml_design* d, FusedArgs a, boo
         if (mode == 0) rc = hess ? launch_fused_t<NB, true, 0>(d, a, grid, st) : launch_fused_t<NB, false, 0>(d, a, grid, st); \
         else rc = hess ? launch_fused_t<NB, true, 1>(d, a, grid, st) : launch_fused_t<NB, false, 1>(d, a, grid, st);           \
         break;
+    if (specialised) {
+        switch (nb16) {
+            case 1: rc = launch_hess_t<1>(d, a, grid, st); break;
+            case 2: rc = launch_hess_t<2>(d, a, grid, st); break;
+            case 3: rc = launch_hess_t<3>(d, a, grid, st); break;
+            default: rc = launch_hess_t<4>(d, a, grid, st); break;
+        }
+    } else
     switch (nb16) {
         FUSED_CASE(1)
         FUSED_CASE(2)

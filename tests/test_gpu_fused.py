@@ -83,6 +83,14 @@ def test_families_links_offset_se(family, link, fast):
     check(got, want)
 
 
+@pytest.mark.parametrize("p", [4, 22, 40, 64])
+def test_symmetric_warp_kernel_variant(p):
+    """fused_eval_kernel<.., HESS, MODE 0> (all warps alike) stays available behind an option."""
+    X, obs, se, off, link, x = make_problem("binomial", 7001, p, seed=p, with_offset=True)
+    want = O.model_eval_fused("binomial", obs, [X], [link], x, offsets=[off])
+    check(gpu_eval("binomial", X, obs, se, off, link, x, options=(("no_warp_specialisation", 1),)), want)
+
+
 def test_general_path_matches_fused():
     X, obs, se, off, link, x = make_problem("binomial", 4099, 37, seed=3, with_offset=True)
     want = O.model_eval_fused("binomial", obs, [X], [link], x, offsets=[off])
