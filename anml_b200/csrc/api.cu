@@ -100,6 +100,7 @@ struct anml_model {
     double* se_owned = nullptr;
     bool prior_enabled = true;
     bool force_generic = false, no_fast = false, no_specialise = false;
+    int helpers = 2;
     cudaStream_t stream = nullptr;
     int sm_count = 0;
     // evaluation buffers (allocated by ensure_buffers once P is known)
@@ -692,6 +693,7 @@ extern "C" int anml_model_set_option(anml_model* m, const char* name, int64_t va
     if (!strcmp(name, "force_generic")) m->force_generic = value != 0;
     else if (!strcmp(name, "no_fast_math_paths")) m->no_fast = value != 0;
     else if (!strcmp(name, "no_warp_specialisation")) m->no_specialise = value != 0;
+    else if (!strcmp(name, "helpers")) m->helpers = (value == 1) ? 1 : 2;
     else return fail(ANML_EINVAL, "unknown option '%s'", name);
     return ANML_OK;
 }
@@ -782,11 +784,11 @@ static int launch_fused_t(const anml_design* d, const FusedArgs& a, int grid, cu
     return ANML_OK;
 }
 
-template <int NB16>
+template <int NB16, int NHELP>
 static int launch_hess_t(const anml_design* d, const FusedArgs& a, int grid, cudaStream_t st) {
-    using C = HessCfg<NB16>;
+    using C = HessCfg<NB16, NHELP>;
     static bool configured = false;
-    auto kern = fused_hess_kernel<NB16>;
+    auto kern = fused_hess_kernel<NB16, NHELP>;
     if (!configured) {
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured = true;
@@ -817,11 +819,12 @@ static int run_fused_block(anml_model* m, const anml_design* d, FusedArgs a, boo
         else rc = hess ? launch_fused_t<NB, true, 1>(d, a, grid, st) : launch_fused_t<NB, false, 1>(d, a, grid, st);           \
         break;
     if (specialised) {
+        const bool two = m->helpers == 2;
         switch (nb16) {
-            case 1: rc = launch_hess_t<1>(d, a, grid, st); break;
-            case 2: rc = launch_hess_t<2>(d, a, grid, st); break;
-            case 3: rc = launch_hess_t<3>(d, a, grid, st); break;
-            default: rc = launch_hess_t<4>(d, a, grid, st); break;
+            case 1: rc = two ? launch_hess_t<1, 2>(d, a, grid, st) : launch_hess_t<1, 1>(d, a, grid, st); break;
+            case 2: rc = two ? launch_hess_t<2, 2>(d, a, grid, st) : launch_hess_t<2, 1>(d, a, grid, st); break;
+            case 3: rc = two ? launch_hess_t<3, 2>(d, a, grid, st) : launch_hess_t<3, 1>(d, a, grid, st); break;
+            default: rc = two ? launch_hess_t<4, 2>(d, a, grid, st) : launch_hess_t<4, 1>(d, a, grid, st); break;
         }
     } else
     switch (nb16) {

@@ -39,13 +39,13 @@
 
 namespace anml {
 
-template <int NB16>
+template <int NB16, int NHELP = 2>
 struct HessCfg {
     static constexpr int TEAMS = 4;
-    static constexpr int HELPERS = 2;  // per team
+    static constexpr int HELPERS = NHELP;  // per team
     static constexpr int WARPS = TEAMS * (1 + HELPERS);
     static constexpr int THREADS = WARPS * 32;
-    static constexpr int REGS_M = 248, REGS_H = 128;  // 4*32*248 + 8*32*128 == 384*168
+    static constexpr int REGS_M = 248, REGS_H = 128;  // NHELP == 2: 4*32*248 + 8*32*128 == 384*168 (NHELP == 1: no transfer needed)
     static constexpr int NB8 = 2 * NB16;
     static constexpr int NT = NB8 * (NB8 + 1) / 2;
     static constexpr int BUF_BYTES = NB16 * 4096;  // NB16 boxes of 32 rows x 128 B
@@ -115,9 +115,9 @@ __device__ __forceinline__ void mma_kstep(double* acc, double* gacc, const doubl
     }
 }
 
-template <int NB16>
-__global__ void __launch_bounds__(384, 1) fused_hess_kernel(const __grid_constant__ CUtensorMap tmap32, const FusedArgs a) {
-    using C = HessCfg<NB16>;
+template <int NB16, int NHELP>
+__global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const __grid_constant__ CUtensorMap tmap32, const FusedArgs a) {
+    using C = HessCfg<NB16, NHELP>;
     constexpr int NB8 = C::NB8, NT = C::NT, NBUF = C::NBUF, TEAMS = C::TEAMS;
 
     extern __shared__ unsigned char smem_raw[];
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(384, 1) fused_hess_kernel(const __grid_constan
 
     if (role == 0) {
         // ============================ tensor warp ============================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::REGS_M));
+        if (NHELP == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::REGS_M));
         auto issue = [&](long long blk_seq, int buf) {
             const long long row0 = (gp + blk_seq * GP) * 32;
             const uint32_t bar = full_u32 + buf * 8;
@@ -228,14 +228,14 @@ __global__ void __launch_bounds__(384, 1) fused_hess_kernel(const __grid_constan
             buf = nbuf;
         }
         // every team is done with its ring: reuse it as reduction scratch
-        asm volatile("bar.sync 1, 384;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(C::THREADS) : "memory");
 #pragma unroll
         for (int e = 0; e < 2 * NT; ++e) scratch[e * 32 + lane] = acc[e];
 #pragma unroll
         for (int jb = 0; jb < NB8; ++jb) scratch[(2 * NT + jb) * 32 + lane] = gacc[jb];
     } else {
         // ============================ helper warps ===========================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_H));
+        if (NHELP == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_H));
         const int hid = role - 1;  // handles the team's blocks i with (i % HELPERS) == hid
         double objacc = 0.0;
         bool bad_domain = false;
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(384, 1) fused_hess_kernel(const __grid_constan
         }
         if (bad_domain) atomicOr(a.status, 1);
         sts64(obj_base + ((team * C::HELPERS + hid) * 32 + lane) * 8, objacc);
-        asm volatile("bar.sync 1, 384;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(C::THREADS) : "memory");
     }
     __syncthreads();
     double* out = a.partials + (size_t)blockIdx.x * C::EL;

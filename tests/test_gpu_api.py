@@ -1,0 +1,213 @@
+"""GPU tests of the anml-compatible Python API (Parameter / SplineVariable /
+Model) against the golden vectors recorded from the reference and against the
+NumPy oracle.  Tolerances: BASELINE.json (obj/grad 1e-10, Hessian 1e-9, fitted
+coefficients 1e-8)."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import anml_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LINKS = {"identity": "Identity", "exp": "Exp", "log": "Log", "expit": "Expit", "logit": "Logit"}
+
+
+def frame_from(X, extra=None):
+    cols = {f"cov{j}": X[:, j + 1] for j in range(X.shape[1] - 1)}
+    cols.update(extra or {})
+    return pd.DataFrame(cols)
+
+
+def make_parameter(p, link="identity", offset=None, priors=None, var_priors=None):
+    from anml_b200.data import Component
+    from anml_b200 import parameter as P
+    from anml_b200.variable import Variable
+
+    variables = [Variable(Component("intercept", default_value=1.0), priors=var_priors)]
+    variables += [Variable(f"cov{j}", priors=var_priors) for j in range(p - 1)]
+    return P.Parameter(variables, transform=getattr(P, LINKS[link])(), offset=offset, priors=priors)
+
+
+# ---- the reference's own known-answer tests for Parameter (tests/parameter/test_main.py:94-153)
+def test_parameter_known_answers():
+    from anml_b200.parameter import Parameter
+    from anml_b200.variable import Variable
+
+    df = pd.DataFrame({"cov1": np.random.randn(5), "cov2": np.random.randn(5)})
+    p = Parameter([Variable("cov1"), Variable("cov2")])
+    x = np.ones(2)
+    assert np.allclose(p.get_params(x, df, order=0), df.sum(axis=1))
+    assert np.allclose(p.get_params(x, df, order=1), df.values)
+    assert np.allclose(p.get_params(x, df, order=2), np.zeros((5, 2, 2)))
+    assert all(v.component.value is not None for v in p.variables)
+    assert p.design_mat is not None and p.design_mat.flags.c_contiguous
+    np.testing.assert_array_equal(p.design_mat, df.values)
+    for cat in ("direct", "linear"):
+        for typ in ("GaussianPrior", "UniformPrior"):
+            assert typ in p.prior_dict[cat]
+    assert p.prior_dict["direct"]["GaussianPrior"].shape == (2, 2)
+    assert p.prior_dict["linear"]["UniformPrior"].mat.shape == (0, 2)
+    assert p.prior_objective(x) == 0.0
+
+
+@pytest.mark.parametrize("case", ["p5_identity", "p5_exp_off", "p7_expit", "p17_expit_off", "p64_expit"])
+def test_get_params_matches_reference_golden(golden, case):
+    X = golden[f"params/{case}/X"]
+    beta = golden[f"params/{case}/beta"]
+    link = str(golden[f"params/{case}/link"])
+    key = f"params/{case}/offset"
+    extra = {"off": golden[key]} if key in golden.files else None
+    par = make_parameter(X.shape[1], link, offset="off" if extra else None)
+    par.attach(frame_from(X, extra))
+    np.testing.assert_array_equal(par.design_mat, X)
+    for order in (0, 1, 2):
+        want = golden[f"params/{case}/order{order}"]
+        got = par.get_params(beta, order=order)
+        assert got.shape == want.shape
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-13 * np.abs(want).max())
+
+
+def test_get_params_domain_and_order_errors():
+    X = np.abs(np.random.default_rng(0).normal(size=(20, 3))) + 0.1
+    par = make_parameter(3, "log")
+    par.attach(frame_from(X))
+    with pytest.raises(ValueError, match="positive"):
+        par.get_params(-np.ones(3))
+    with pytest.raises(ValueError, match="Order"):
+        par.get_params(np.ones(3), order=3)
+    assert np.all(np.isfinite(par.get_params(np.ones(3), order=2)))
+
+
+@pytest.mark.parametrize("case,fam", [("gauss_p4", "gaussian"), ("binom_p6", "binomial"), ("binom_p64", "binomial"),
+                                      ("poisson_p5_off", "poisson"), ("gauss_exp_p3", "gaussian"), ("meanvar_p5", "gaussian_meanvar")])
+def test_model_matches_reference_composition(golden, case, fam):
+    from anml_b200.data import DataExample
+    from anml_b200.model import Model
+    from anml_b200.prior import GaussianPrior
+
+    X = golden[f"model/{case}/X"]
+    links = str(golden[f"model/{case}/links"]).split(",")
+    key = f"model/{case}/offset"
+    extra = {"obs": golden[f"model/{case}/obs"], "se": golden[f"model/{case}/se"]}
+    if key in golden.files:
+        extra["off"] = golden[key]
+    sd = float(golden[f"model/{case}/prior_sd"])
+    vp = [GaussianPrior(mean=0.0, sd=sd)] if sd > 0 else None
+    pars = [make_parameter(X.shape[1], l, offset="off" if "off" in extra else None, var_priors=vp) for l in links]
+    model = Model(fam, DataExample("obs", "se"), pars)
+    model.attach(frame_from(X, extra))
+    x = golden[f"model/{case}/x"]
+    obj, grad, hess = model.objective(x), model.gradient(x), model.hessian(x)
+    assert model.num_evaluations == 1  # the three callbacks share one device evaluation
+    ow, gw, hw = float(golden[f"model/{case}/obj"]), golden[f"model/{case}/grad"], golden[f"model/{case}/hess"]
+    assert abs(obj - ow) <= 1e-10 * abs(ow)
+    assert np.abs(grad - gw).max() <= 1e-10 * np.abs(gw).max()
+    assert np.abs(hess - hw).max() <= 1e-9 * np.abs(hw).max()
+    if fam == "gaussian_meanvar":
+        assert pars[0].device_design is pars[1].device_design  # same columns -> one matrix in HBM
+
+
+def test_config1_trust_constr_fit_matches_reference(golden):
+    """BASELINE config #1: Gaussian, intercept + 3 covariates, 10k rows; fitted
+    coefficients within 1e-8 of the fit driven by the reference's callbacks."""
+    from anml_b200.data import DataExample
+    from anml_b200.model import Model
+
+    n, p = 10_000, 4
+    r = np.random.default_rng(int(golden["c1/seed"]))
+    Xc = r.normal(size=(n, p - 1))
+    beta_true = r.normal(size=p) * 0.1
+    np.testing.assert_array_equal(beta_true, golden["c1/beta_true"])
+    obs = beta_true[0] + Xc @ beta_true[1:] + 0.1 * r.normal(size=n)
+    df = pd.DataFrame({f"cov{j}": Xc[:, j] for j in range(p - 1)})
+    df["obs"] = obs
+    model = Model("gaussian", DataExample("obs", "obs_se"), [make_parameter(p)])
+    model.attach(df)
+    assert abs(model.objective(np.zeros(p)) - float(golden["c1/obj_at_zero"])) <= 1e-10 * float(golden["c1/obj_at_zero"])
+    res = model.fit(np.zeros(p))
+    assert np.abs(res.x - golden["c1/coef"]).max() <= 1e-8
+    assert np.abs(res.x - beta_true).max() < 0.01
+
+
+def test_model_bounds_and_constraints_reach_the_solver():
+    from anml_b200.data import Component, DataExample
+    from anml_b200.model import Model
+    from anml_b200.parameter import Parameter
+    from anml_b200.prior import UniformPrior
+    from anml_b200.variable import Variable
+
+    r = np.random.default_rng(4)
+    n = 2000
+    df = pd.DataFrame({"a": r.normal(size=n), "b": r.normal(size=n)})
+    df["obs"] = 1.0 + 2.0 * df["a"] - 1.0 * df["b"] + 0.01 * r.normal(size=n)
+    vs = [Variable(Component("intercept", default_value=1.0)), Variable("a", priors=[UniformPrior(lb=0.0, ub=1.5)]), Variable("b")]
+    par = Parameter(vs, priors=[UniformPrior(lb=[-0.5], ub=[0.5], mat=np.array([[0.0, 1.0, 1.0]]))])
+    model = Model("gaussian", DataExample("obs", "obs_se"), [par])
+    model.attach(df)
+    b = model.bounds()
+    assert b.ub[1] == 1.5 and np.isinf(b.ub[0])
+    assert len(model.constraints()) == 1
+    res = model.fit(options={"gtol": 1e-8})
+    assert res.x[1] <= 1.5 + 1e-6  # the bound binds (unconstrained optimum is 2.0)
+    assert abs(res.x[1] + res.x[2]) <= 0.5 + 1e-6
+
+
+def test_model_requires_attach_and_validates():
+    from anml_b200.data import DataExample
+    from anml_b200.model import Model
+
+    with pytest.raises(ValueError):
+        Model("binomial", DataExample("obs", "se"), [make_parameter(2), make_parameter(2)])
+    with pytest.raises(ValueError):
+        Model("nope", DataExample("obs", "se"), [make_parameter(2)])
+    m = Model("binomial", DataExample("obs", "se"), [make_parameter(2)])
+    with pytest.raises(ValueError, match="attach"):
+        m.objective(np.zeros(2))
+
+
+def test_spline_variable_in_a_parameter_and_smoothing_prior():
+    """BASELINE config #3 in miniature: SplineGetter (rel_domain knots, degree 3)
+    + SplinePriorGetter(GaussianPrior, order=2) smoothing, Gaussian likelihood."""
+    from anml_b200.data import DataExample
+    from anml_b200.getter import SplineGetter, SplinePriorGetter
+    from anml_b200.model import Model
+    from anml_b200.parameter import Parameter
+    from anml_b200.prior import GaussianPrior, Prior
+    from anml_b200.variable import SplineVariable
+    from anml_b200.xspline import XSpline
+
+    r = np.random.default_rng(20261019 + 3)
+    n = 30_000
+    xs = r.uniform(0, 1, size=n)
+    df = pd.DataFrame({"x": xs, "obs": np.sin(2 * np.pi * xs) + 0.1 * r.normal(size=n)})
+    sv = SplineVariable("x", SplineGetter(np.linspace(0, 1, 20), degree=3, knots_type="rel_domain"),
+                        priors=[SplinePriorGetter(GaussianPrior(0.0, 50.0), size=100, order=2)])
+    assert sv.size == 22
+    par = Parameter([sv])
+    model = Model("gaussian", DataExample("obs", "obs_se"), [par])
+    model.attach(df)
+    assert isinstance(sv.spline, XSpline) and isinstance(sv.priors[0], Prior) and sv.priors[0].mat.shape == (100, 22)
+    knots = O.spline_knots(np.linspace(0, 1, 20), "rel_domain", xs)
+    np.testing.assert_array_equal(sv.spline.knots, knots)
+    D = par.design_mat
+    assert D.shape == (n, 22)
+    np.testing.assert_array_equal(D, O.spline_design(knots, 3, xs))  # bit-exact basis inside the knot span
+    pts = O.spline_prior_points(knots, 100)
+    M = O.spline_design(knots, 3, pts, order=2)
+    np.testing.assert_allclose(sv.priors[0].mat, M, rtol=0, atol=1e-12 * np.abs(M).max())
+    lin = par.prior_dict["linear"]["GaussianPrior"]
+    x = r.normal(size=22) * 0.3
+    want = O.model_eval_fused("gaussian", df["obs"].to_numpy(), [D], ["identity"], x,
+                              priors=[{"linear": (lin.mean, lin.sd, lin.mat)}])
+    got = model.evaluate(x)
+    assert abs(got[0] - want[0]) <= 1e-10 * abs(want[0])
+    assert np.abs(got[1] - want[1]).max() <= 1e-10 * np.abs(want[1]).max()
+    assert np.abs(got[2] - want[2]).max() <= 1e-9 * np.abs(want[2]).max()
+    # host prior path of the Parameter agrees with the device prior epilogue
+    nop = O.model_eval_fused("gaussian", df["obs"].to_numpy(), [D], ["identity"], x)
+    assert abs((got[0] - nop[0]) - par.prior_objective(x)) <= 1e-9 * abs(got[0])
+    res = model.fit(options={"gtol": 1e-8, "maxiter": 200})
+    assert np.abs(model.gradient(res.x)).max() < 1e-5  # a stationary point of the penalised likelihood
+    fitted = D @ res.x
+    assert np.sqrt(np.mean((fitted - np.sin(2 * np.pi * xs)) ** 2)) < 0.05

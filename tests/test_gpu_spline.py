@@ -1,0 +1,88 @@
+"""GPU spline-basis kernel: knot-interval indices bit-exact, basis values
+bit-exact inside the knot span, derivatives and extrapolation within 1e-13."""
+import numpy as np
+import pytest
+
+from oracle import anml_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def sample_points(knots, n, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(knots[0], knots[-1], size=n)
+    # exact knots, end points, and the floats adjacent to each knot
+    special = np.concatenate([knots, np.nextafter(knots, -np.inf), np.nextafter(knots, np.inf)])
+    special = special[(special >= knots[0]) & (special <= knots[-1])]
+    return np.concatenate([x, special])
+
+
+@pytest.mark.parametrize("degree", [1, 2, 3, 5])
+@pytest.mark.parametrize("nk", [2, 5, 20])
+def test_basis_and_interval_index_bit_exact(degree, nk):
+    from anml_b200.xspline import XSpline
+
+    knots = np.sort(np.random.default_rng(nk).uniform(-2, 3, size=nk))
+    x = sample_points(knots, 100_000 if nk == 20 else 5000, seed=degree)
+    D, idx = XSpline(knots, degree).get_design_mat(x, return_index=True)
+    want, widx = O.spline_design(knots, degree, x, return_index=True)
+    assert idx.dtype == np.int32
+    np.testing.assert_array_equal(idx, widx)
+    np.testing.assert_array_equal(D, want)
+    assert (np.count_nonzero(D, axis=1) <= degree + 1).all()
+    np.testing.assert_allclose(D.sum(axis=1), 1.0, atol=1e-13)
+
+
+def test_config3_interval_indices_one_million_rows():
+    """indices compared bit-exactly on a 1e6-row sample incl.
+    exact-knot and end-point values (20 knots on [0, 1], degree 3 -> 22 bases)."""
+    from anml_b200.xspline import XSpline
+
+    knots = np.linspace(0.0, 1.0, 20)
+    x = sample_points(knots, 1_000_000, seed=20261019 + 3)
+    sp = XSpline(knots, 3)
+    idx = sp.interval_index(x)
+    np.testing.assert_array_equal(idx, O.spline_interval_index(knots, x))
+    np.testing.assert_array_equal(sp.interval_index(np.array([knots[0], knots[-1], knots[5]])), [0, 18, 5])
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+def test_derivative_orders(order):
+    from anml_b200.xspline import XSpline
+
+    knots = np.linspace(0.0, 2.0, 9)
+    x = sample_points(knots, 3000, seed=order)
+    D = XSpline(knots, 3).get_design_mat(x, order=order)
+    want = O.spline_design(knots, 3, x, order=order)
+    np.testing.assert_allclose(D, want, rtol=0, atol=1e-13 * max(np.abs(want).max(), 1.0))
+    if order > 3:
+        assert not D.any()
+
+
+@pytest.mark.parametrize("ldeg,rdeg", [(0, 0), (1, 1), (2, 3), (3, 0)])
+@pytest.mark.parametrize("order", [0, 1])
+def test_extrapolation(ldeg, rdeg, order):
+    from anml_b200.xspline import XSpline
+
+    knots = np.array([0.0, 0.3, 0.7, 1.5])
+    x = np.concatenate([np.linspace(-1.0, 2.5, 71), knots])
+    D, idx = XSpline(knots, 3, ldegree=ldeg, rdegree=rdeg).get_design_mat(x, order=order, return_index=True)
+    want, widx = O.spline_design(knots, 3, x, order=order, ldegree=ldeg, rdegree=rdeg, return_index=True)
+    np.testing.assert_array_equal(idx, widx)
+    np.testing.assert_allclose(D, want, rtol=0, atol=1e-12 * max(np.abs(want).max(), 1.0))
+
+
+def test_spline_argument_errors():
+    from anml_b200 import _native
+    from anml_b200.xspline import XSpline
+
+    with pytest.raises(ValueError):
+        XSpline([1.0], 3)
+    with pytest.raises(ValueError):
+        XSpline([1.0, 0.0], 3)
+    with pytest.raises(ValueError):
+        _native.spline_design([0.5], [0.0, 0.0], 3)  # empty knot span
+    with pytest.raises(NotImplementedError):
+        _native.spline_design([0.5], [0.0, 1.0], 9)  # degree above the kernel's limit
+    out = _native.spline_design(np.empty(0), [0.0, 1.0], 3)
+    assert out.shape == (0, 4)

@@ -26,6 +26,9 @@ def main():
     model = N.NativeModel(n, "binomial", 1)
     model.set_param(0, design, N.LINK_CODES["Expit"])
     model.set_obs(dev_ptr=obs.data_ptr(), keepalive=obs)
+    for kv in sys.argv[4:]:
+        k, v = kv.split("=")
+        model.set_option(k, int(v))
     x = (0.5 * beta_true).cpu().numpy()
     want = N.WANT_OBJ | N.WANT_GRAD | (N.WANT_HESS if want_h else 0)
     for _ in range(3):
