@@ -123,9 +123,10 @@ int anml_model_num_coefs(const anml_model* m, int* total);
  * NULL where not wanted.  Log/Logit domain violations return ANML_EDOMAIN. */
 int anml_model_eval(anml_model* m, const double* x_host, int want, double* obj, double* grad, double* hess);
 /* Same, leaving the packed result [obj | grad(P) | hess(P*P) | domain flag] in
- * device memory (packed_dev, 2 + P + P*P doubles) on `stream` (a cudaStream_t,
- * NULL = the model's own stream) without synchronising: the row-sharded caller
- * all-reduces it over NCCL before reading it. */
+ * device memory (packed_dev, 2 + P + P*P doubles) on `stream` (a cudaStream_t;
+ * NULL = the model's own stream, cudaStreamLegacy (0x1) = the legacy default
+ * stream) without synchronising: the row-sharded caller all-reduces it over
+ * NCCL before reading it. */
 int anml_model_eval_async(anml_model* m, const double* x_host, int want, double* packed_dev, void* stream);
 /* CUDA-event time of the dominant kernel, accumulated over evaluations since
  * the last reset (what bench.py reports as roofline.achieved) */
