@@ -17,6 +17,7 @@
 #include "fused_hess.cuh"
 #include "generic.cuh"
 #include "spline.cuh"
+#include "wide_hessian.cuh"
 
 using namespace anml;
 
@@ -866,13 +867,50 @@ static int run_priors(anml_model* m, int want, cudaStream_t st) {
 }
 
 static int eval_general(anml_model* m, int want, cudaStream_t st);
+static EventPair* next_events(anml_model* m);
 
 // H block (row_off, col_off) = Xa^T diag(w) Xb for designs wider than 64 columns
-// or two different designs.
+// or two different designs (wide_hessian.cuh).
 static int run_wide_hessian(anml_model* m, const anml_design* da, const anml_design* db, const double* w, int row_off, int col_off,
                             cudaStream_t st) {
-    (void)m; (void)da; (void)db; (void)w; (void)row_off; (void)col_off; (void)st;
-    return fail(ANML_EUNSUPPORTED, "Hessian blocks wider than 64 columns are not implemented yet");
+    const int nba = (da->p + 127) / 128, nbb = (db->p + 127) / 128;
+    const bool symmetric = (da == db) && (row_off == col_off);
+    const int npairs = symmetric ? nba * (nba + 1) / 2 : nba * nbb;
+    long long S = (2LL * m->sm_count + npairs - 1) / npairs;
+    if (S < 1) S = 1;
+    long long chunk_rows = (m->n_pad + S - 1) / S;
+    chunk_rows = round_up_ll(chunk_rows, 16);
+    if (chunk_rows < 16) chunk_rows = 16;
+    S = (m->n_pad + chunk_rows - 1) / chunk_rows;
+    const long long need = S * npairs * 16384LL;
+    if (need > m->wide_len) {
+        CU_TRY(cudaStreamSynchronize(st));
+        if (m->d_wide) CU_TRY(cudaFree(m->d_wide));
+        m->d_wide = nullptr;
+        m->wide_len = 0;
+        CU_TRY(cudaMalloc(&m->d_wide, (size_t)need * sizeof(double)));
+        m->wide_len = need;
+    }
+    static bool configured = false;
+    if (!configured) {
+        CU_TRY(cudaFuncSetAttribute(wide_hessian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WIDE_SMEM_BYTES));
+        configured = true;
+    }
+    WideArgs a;
+    a.n_pad = m->n_pad; a.chunk_rows = chunk_rows; a.npairs = npairs; a.nbj = nbb; a.symmetric = symmetric ? 1 : 0;
+    a.shared_panels = (da == db) ? 1 : 0; a.w = w; a.partials = m->d_wide;
+    EventPair* ep = next_events(m);
+    if (ep) CU_TRY(cudaEventRecord(ep->a, st));
+    wide_hessian_kernel<<<(unsigned)(S * npairs), WIDE_THREADS, WIDE_SMEM_BYTES, st>>>(da->tmap, db->tmap, a);
+    CU_TRY(cudaGetLastError());
+    if (ep) CU_TRY(cudaEventRecord(ep->b, st));
+    const long long total = (long long)npairs * 16384;
+    wide_reduce_kernel<<<grid_for(total, 256, m->sm_count, 8), 256, 0, st>>>(m->d_wide, (int)S, npairs, nbb, symmetric ? 1 : 0, da->p, db->p,
+                                                                            m->d_packed + 1 + m->P, m->P, row_off, col_off);
+    CU_TRY(cudaGetLastError());
+    m->main_launches += 1;
+    m->all_launches += 2;
+    return ANML_OK;
 }
 
 static int eval_on_stream(anml_model* m, const double* x_host, int want, cudaStream_t st) {

@@ -125,3 +125,43 @@ def test_log_link_domain_error():
     X, obs, se, off, link, x = make_problem("gaussian", 100, 3, seed=2)
     with pytest.raises(ValueError):
         gpu_eval("gaussian", X, np.abs(obs) + 1, se, off, "log", -np.abs(x) - 1.0)
+
+
+@pytest.mark.parametrize("n,p", [(3000, 65), (5001, 128), (2047, 200), (1500, 257), (700, 520)])
+def test_wide_designs_use_the_blocked_hessian_kernel(n, p):
+    """p > 64: general path (linpred -> rowterms -> xtr + wide_hessian_kernel)."""
+    X, obs, se, off, link, x = make_problem("binomial", n, p, seed=p, with_offset=True)
+    x = x * (4.0 / np.sqrt(p))  # keep |X beta| moderate for wide designs
+    want = O.model_eval_fused("binomial", obs, [X], [link], x, offsets=[off])
+    check(gpu_eval("binomial", X, obs, se, off, link, x), want)
+
+
+def gpu_eval_meanvar(X0, X1, obs, x, links=("identity", "exp"), share=False):
+    from anml_b200 import _native as N
+
+    n = X0.shape[0]
+    d0 = N.Design(n, X0.shape[1]); d0.set_columns(0, X0)
+    if share:
+        d1 = d0
+    else:
+        d1 = N.Design(n, X1.shape[1]); d1.set_columns(0, X1)
+    model = N.NativeModel(n, "gaussian_meanvar", 2)
+    model.set_param(0, d0, N.LINK_CODES[LINK_NAME[links[0]]])
+    model.set_param(1, d1, N.LINK_CODES[LINK_NAME[links[1]]])
+    model.set_obs(obs)
+    return model.eval(x)
+
+
+@pytest.mark.parametrize("p0,p1,share", [(5, 5, True), (5, 7, False), (64, 64, True), (70, 70, True), (40, 130, False)])
+def test_two_parameter_mean_variance_model(p0, p1, share):
+    rng = np.random.default_rng(p0 * 1000 + p1)
+    n = 2500
+    X0 = rng.normal(size=(n, p0)); X0[:, 0] = 1.0
+    X1 = X0 if share else rng.normal(size=(n, p1))
+    X1[:, 0] = 1.0
+    b0 = rng.normal(size=p0) * 0.2 / np.sqrt(p0 / 5)
+    b1 = rng.normal(size=p1) * 0.1 / np.sqrt(p1 / 5)
+    obs = X0 @ b0 + np.exp(0.5 * (X1 @ b1)) * rng.normal(size=n)
+    x = np.concatenate([0.7 * b0, 0.7 * b1])
+    want = O.model_eval_fused("gaussian_meanvar", obs, [X0, X1], ["identity", "exp"], x)
+    check(gpu_eval_meanvar(X0, X1, obs, x, share=share), want)
