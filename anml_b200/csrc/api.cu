@@ -102,6 +102,8 @@ struct anml_model {
     bool prior_enabled = true;
     bool force_generic = false, no_fast = false, no_specialise = false;
     int helpers = 2;
+    int debug_bits = 0;  // DEBUG switches of fused_hess_kernel (timing experiments only)
+    bool force_signed = false;
     cudaStream_t stream = nullptr;
     int sm_count = 0;
     // evaluation buffers (allocated by ensure_buffers once P is known)
@@ -695,6 +697,8 @@ extern "C" int anml_model_set_option(anml_model* m, const char* name, int64_t va
     else if (!strcmp(name, "no_fast_math_paths")) m->no_fast = value != 0;
     else if (!strcmp(name, "no_warp_specialisation")) m->no_specialise = value != 0;
     else if (!strcmp(name, "helpers")) m->helpers = (value == 1) ? 1 : 2;
+    else if (!strcmp(name, "debug_skip_helpers")) m->debug_bits = (int)value;  // 1: all helper math, 2: link/family, 4: pass 2
+    else if (!strcmp(name, "force_signed_weights")) m->force_signed = value != 0;
     else return fail(ANML_EINVAL, "unknown option '%s'", name);
     return ANML_OK;
 }
@@ -785,11 +789,11 @@ static int launch_fused_t(const anml_design* d, const FusedArgs& a, int grid, cu
     return ANML_OK;
 }
 
-template <int NB16, int NHELP>
+template <int NB16, int NHELP, bool SIGNED>
 static int launch_hess_t(const anml_design* d, const FusedArgs& a, int grid, cudaStream_t st) {
     using C = HessCfg<NB16, NHELP>;
     static bool configured = false;
-    auto kern = fused_hess_kernel<NB16, NHELP>;
+    auto kern = fused_hess_kernel<NB16, NHELP, SIGNED>;
     if (!configured) {
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured = true;
@@ -797,6 +801,13 @@ static int launch_hess_t(const anml_design* d, const FusedArgs& a, int grid, cud
     kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(d->tmap32, a);
     CU_TRY(cudaGetLastError());
     return ANML_OK;
+}
+
+// canonical link/family pairs have Hessian weights w > 0 (no sign handling in the tensor warp)
+static bool weights_positive(int family, int link, bool fast) {
+    (void)fast;
+    return (family == ANML_FAMILY_BINOMIAL && link == ANML_LINK_EXPIT) || (family == ANML_FAMILY_GAUSSIAN && link == ANML_LINK_IDENTITY) ||
+           (family == ANML_FAMILY_POISSON && link == ANML_LINK_EXP);
 }
 
 // fused kernel + partial reduction + layout undo for one parameter block
@@ -821,12 +832,19 @@ static int run_fused_block(anml_model* m, const anml_design* d, FusedArgs a, boo
         break;
     if (specialised) {
         const bool two = m->helpers == 2;
+        const bool sgn = !weights_positive(a.family, a.link, a.fast != 0) || m->force_signed;
+#define HESS_CASE(NB)                                                                                         \
+    case NB:                                                                                                  \
+        if (two) rc = sgn ? launch_hess_t<NB, 2, true>(d, a, grid, st) : launch_hess_t<NB, 2, false>(d, a, grid, st); \
+        else rc = sgn ? launch_hess_t<NB, 1, true>(d, a, grid, st) : launch_hess_t<NB, 1, false>(d, a, grid, st);     \
+        break;
         switch (nb16) {
-            case 1: rc = two ? launch_hess_t<1, 2>(d, a, grid, st) : launch_hess_t<1, 1>(d, a, grid, st); break;
-            case 2: rc = two ? launch_hess_t<2, 2>(d, a, grid, st) : launch_hess_t<2, 1>(d, a, grid, st); break;
-            case 3: rc = two ? launch_hess_t<3, 2>(d, a, grid, st) : launch_hess_t<3, 1>(d, a, grid, st); break;
-            default: rc = two ? launch_hess_t<4, 2>(d, a, grid, st) : launch_hess_t<4, 1>(d, a, grid, st); break;
+            HESS_CASE(1)
+            HESS_CASE(2)
+            HESS_CASE(3)
+            HESS_CASE(4)
         }
+#undef HESS_CASE
     } else
     switch (nb16) {
         FUSED_CASE(1)
@@ -934,7 +952,7 @@ static int eval_on_stream(anml_model* m, const double* x_host, int want, cudaStr
     const anml_design* d0 = m->par[0].design;
     if (m->K == 1 && d0->p <= 64 && !m->force_generic) {
         FusedArgs a;
-        a.n = m->n; a.p = d0->p; a.link = m->par[0].link; a.family = m->family; a.fast = m->no_fast ? 0 : 1;
+        a.n = m->n; a.p = d0->p; a.link = m->par[0].link; a.family = m->family; a.fast = (m->no_fast ? 0 : 1) | (m->debug_bits << 1);
         a.beta = m->d_beta + m->par[0].pad_off; a.obs = m->obs; a.se = m->se; a.offset = m->par[0].offset;
         a.rvec = nullptr; a.wvec = nullptr; a.partials = nullptr; a.status = nullptr;
         TRY(run_fused_block(m, d0, a, hess, 0, 0, 0, true, false, true, st));

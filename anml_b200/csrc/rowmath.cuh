@@ -62,34 +62,45 @@ __device__ __forceinline__ double link_order(int link, double y, int order, bool
 // so that grad = X^T r and Hessian = X^T diag(w) X  (SURVEY.md 3.3).
 struct RowTerms1 {
     double l, r, w;
+    double sw;  // sqrt(|w|), filled only when asked for
     bool ok;
 };
 
+template <bool WANT_SQRT = false>
 __device__ __forceinline__ RowTerms1 row_terms1(int family, int link, bool fast, double y, double obs, double se) {
     RowTerms1 o;
     o.ok = true;
+    o.sw = 0.0;
     if (fast && family == FAM_BINOMIAL && link == LINK_EXPIT) {
-        // canonical logistic: one exp, one log, one reciprocal per row
-        const double z = exp(-y);
-        const double q = 1.0 / (1.0 + z);
-        o.l = log1p(z) + (1.0 - obs) * y;
+        // canonical logistic: one exp, one log, one reciprocal per row.
+        // h = exp(-y/2): z = h^2 and sqrt(w) = h q come for free (no sqrt).
+        const double h = exp(-0.5 * y);
+        const double z = h * h;
+        const double s = 1.0 + z;
+        const double q = 1.0 / s;
+        o.l = log(s) + (1.0 - obs) * y;
         o.r = q - obs;
-        o.w = z * q * q;
+        o.sw = h * q;
+        o.w = o.sw * o.sw;
         return o;
     }
     if (fast && family == FAM_GAUSSIAN && link == LINK_IDENTITY) {
-        const double iv = 1.0 / (se * se);
+        const double is = 1.0 / se;
+        const double iv = is * is;
         const double res = y - obs;
         o.r = res * iv;
         o.w = iv;
+        o.sw = is;
         o.l = 0.5 * res * o.r;
         return o;
     }
     if (fast && family == FAM_POISSON && link == LINK_EXP) {
-        const double lam = exp(y);
+        const double h = exp(0.5 * y);
+        const double lam = h * h;
         o.l = lam - obs * y;
         o.r = lam - obs;
         o.w = lam;
+        o.sw = h;
         return o;
     }
     const LinkVal f = link_eval(link, y);
@@ -115,6 +126,7 @@ __device__ __forceinline__ RowTerms1 row_terms1(int family, int link, bool fast,
     o.l = l;
     o.r = d1 * f.d1;
     o.w = d2 * f.d1 * f.d1 + d1 * f.d2;
+    if (WANT_SQRT) o.sw = sqrt(fabs(o.w));
     return o;
 }
 
