@@ -1007,13 +1007,12 @@ static int eval_general(anml_model* m, int want, cudaStream_t st) {
             TRY(run_fused_block(m, d, a, hess, 1, m->par[k].off, m->par[k].off, true, true, true, st));
         } else {
             // gradient: streaming X^T r
-            const int warps = 4;
-            int grid = m->sm_count;
-            if ((long long)grid * warps > d->n) grid = (int)((d->n + warps - 1) / warps);
+            const int nchunks = (int)((d->ld + 63) / 64);
+            int grid = (8 * m->sm_count + nchunks - 1) / nchunks;
+            if ((long long)grid * 8 > d->n) grid = (int)((d->n + 7) / 8);
             if (grid < 1) grid = 1;
-            const size_t smem = (size_t)warps * d->ld * sizeof(double);
-            if (smem > 48 * 1024) return fail(ANML_EUNSUPPORTED, "design wider than 1536 columns is not supported by the gradient kernel");
-            xtr_kernel<<<grid, warps * 32, smem, st>>>(d->X, d->n, d->ld, m->vec[2 + k], m->d_partials);
+            if ((long long)grid * d->ld > m->partials_len) grid = (int)(m->partials_len / d->ld);
+            xtr_kernel<<<dim3(grid, nchunks), 256, 0, st>>>(d->X, d->n, d->ld, m->vec[2 + k], m->d_partials);
             CU_TRY(cudaGetLastError());
             column_sum_kernel<<<(d->p + 255) / 256, 256, 0, st>>>(m->d_partials, grid, d->ld, d->p, m->d_packed + 1 + m->par[k].off);
             CU_TRY(cudaGetLastError());

@@ -135,37 +135,51 @@ __global__ void sum_partials_kernel(const double* __restrict__ partials, int cou
     }
 }
 
-// g = X^T r for any p.  Each warp streams whole rows (lanes over column pairs);
-// per-CTA partial g written to partials[cta][ld]; column_sum_kernel finishes.
+// g = X^T r for any p.  grid = (row CTAs, 64-column chunks).  Each warp owns one
+// 64-column chunk (one double2 per lane) and strides over rows with 8 independent
+// 512-byte loads in flight; per-CTA partials, column_sum_kernel finishes (fixed order).
 __global__ void __launch_bounds__(256) xtr_kernel(const double* __restrict__ X, long long n, long long ld,
                                                   const double* __restrict__ r, double* __restrict__ partials) {
-    extern __shared__ double gs[];  // [warps][ld]
+    __shared__ double gs[8][64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    const int npairs = (int)(ld >> 1);
-    double* mine = gs + (size_t)warp * ld;
-    for (int c = lane; c < (int)ld; c += 32) mine[c] = 0.0;
-    __syncwarp();
+    const int c = blockIdx.y * 32 + lane;  // column pair
+    const bool live = 2 * c < ld;
+    double ax = 0.0, ay = 0.0;
     const long long w0 = (long long)blockIdx.x * nw + warp, wstride = (long long)gridDim.x * nw;
-    // columns in chunks of 64 (one double2 per lane), rows strided over warps
-    for (int c0 = 0; c0 < npairs; c0 += 32) {
-        const int c = c0 + lane;
-        double ax = 0.0, ay = 0.0;
-        if (c < npairs) {
-            for (long long row = w0; row < n; row += wstride) {
-                const double rv = r[row];
-                const double2 v = ldg_stream2(X + row * ld + 2 * c);
-                ax = fma(rv, v.x, ax);
-                ay = fma(rv, v.y, ay);
+    long long row = w0;
+    if (live) {
+        const double* xp = X + 2 * c;
+        for (; row + 7 * wstride < n; row += 8 * wstride) {
+            double2 v[8];
+            double rv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                v[u] = ldg_stream2(xp + (row + u * wstride) * ld);
+                rv[u] = r[row + u * wstride];
             }
-            mine[2 * c] = ax;
-            mine[2 * c + 1] = ay;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                ax = fma(rv[u], v[u].x, ax);
+                ay = fma(rv[u], v[u].y, ay);
+            }
+        }
+        for (; row < n; row += wstride) {
+            const double rv = r[row];
+            const double2 v = ldg_stream2(xp + row * ld);
+            ax = fma(rv, v.x, ax);
+            ay = fma(rv, v.y, ay);
         }
     }
+    gs[warp][2 * lane] = ax;
+    gs[warp][2 * lane + 1] = ay;
     __syncthreads();
-    for (int c = threadIdx.x; c < (int)ld; c += blockDim.x) {
-        double s = 0.0;
-        for (int w = 0; w < nw; ++w) s += gs[(size_t)w * ld + c];
-        partials[(size_t)blockIdx.x * ld + c] = s;
+    if (threadIdx.x < 64) {
+        const int col = blockIdx.y * 64 + threadIdx.x;
+        if (col < ld) {
+            double s = 0.0;
+            for (int w = 0; w < nw; ++w) s += gs[w][threadIdx.x];
+            partials[(size_t)blockIdx.x * ld + col] = s;
+        }
     }
 }
 
