@@ -102,7 +102,6 @@ struct anml_model {
     bool prior_enabled = true;
     bool force_generic = false, no_fast = false, no_specialise = false;
     int helpers = 2;
-    int debug_bits = 0;  // DEBUG switches of fused_hess_kernel (timing experiments only)
     bool force_signed = false;
     cudaStream_t stream = nullptr;
     int sm_count = 0;
@@ -697,7 +696,6 @@ extern "C" int anml_model_set_option(anml_model* m, const char* name, int64_t va
     else if (!strcmp(name, "no_fast_math_paths")) m->no_fast = value != 0;
     else if (!strcmp(name, "no_warp_specialisation")) m->no_specialise = value != 0;
     else if (!strcmp(name, "helpers")) m->helpers = (value == 1) ? 1 : 2;
-    else if (!strcmp(name, "debug_skip_helpers")) m->debug_bits = (int)value;  // 1: all helper math, 2: link/family, 4: pass 2
     else if (!strcmp(name, "force_signed_weights")) m->force_signed = value != 0;
     else return fail(ANML_EINVAL, "unknown option '%s'", name);
     return ANML_OK;
@@ -789,11 +787,11 @@ static int launch_fused_t(const anml_design* d, const FusedArgs& a, int grid, cu
     return ANML_OK;
 }
 
-template <int NB16, int NHELP, bool SIGNED>
+template <int NB16, int NHELP, bool SIGNED, int MODE>
 static int launch_hess_t(const anml_design* d, const FusedArgs& a, int grid, cudaStream_t st) {
     using C = HessCfg<NB16, NHELP>;
     static bool configured = false;
-    auto kern = fused_hess_kernel<NB16, NHELP, SIGNED>;
+    auto kern = fused_hess_kernel<NB16, NHELP, SIGNED, MODE>;
     if (!configured) {
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured = true;
@@ -810,13 +808,46 @@ static bool weights_positive(int family, int link, bool fast) {
            (family == ANML_FAMILY_POISSON && link == ANML_LINK_EXP);
 }
 
+// Two-parameter model over ONE design with p <= 64: a single streaming pass computes both
+// linear predictors, the row terms (r0, r1, w00, w01, w11 -> device vectors) and the objective.
+static int run_dual_terms(anml_model* m, cudaStream_t st) {
+    const anml_design* d = m->par[0].design;
+    const int nb16 = (d->p + 15) / 16;
+    const long long nblk = (d->n + 31) / 32;
+    int grid = (int)((nblk + 7) / 8);
+    if (grid > m->sm_count) grid = m->sm_count;
+    if (grid < 1) grid = 1;
+    FusedArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = m->n; a.p = d->p; a.link = m->par[0].link; a.link1 = m->par[1].link; a.family = m->family;
+    a.beta = m->d_beta + m->par[0].pad_off; a.beta1 = m->d_beta + m->par[1].pad_off;
+    a.obs = m->obs; a.offset = m->par[0].offset; a.offset1 = m->par[1].offset;
+    a.out_r0 = m->vec[2]; a.out_r1 = m->vec[3]; a.out_w00 = m->vec[4]; a.out_w01 = m->vec[5]; a.out_w11 = m->vec[6];
+    a.partials = m->d_partials; a.status = m->d_status;
+    int rc = ANML_OK;
+    switch (nb16) {
+        case 1: rc = launch_fused_t<1, false, 2>(d, a, grid, st); break;
+        case 2: rc = launch_fused_t<2, false, 2>(d, a, grid, st); break;
+        case 3: rc = launch_fused_t<3, false, 2>(d, a, grid, st); break;
+        default: rc = launch_fused_t<4, false, 2>(d, a, grid, st); break;
+    }
+    TRY(rc);
+    const int el = fused_el(nb16, false);
+    reduce_partials_kernel<<<(el + 255) / 256, 256, 0, st>>>(m->d_partials, grid, el, m->d_reduced);
+    CU_TRY(cudaGetLastError());
+    assemble_kernel<<<1, 256, 0, st>>>(m->d_reduced, nb16, 0, d->p, m->d_packed, m->P, 0, 0, 0, 0);  // objective only
+    CU_TRY(cudaGetLastError());
+    m->all_launches += 3;
+    return ANML_OK;
+}
+
 // fused kernel + partial reduction + layout undo for one parameter block
 static int run_fused_block(anml_model* m, const anml_design* d, FusedArgs a, bool hess, int mode, int row_off, int col_off,
                            bool write_grad, bool add_obj, bool timed, cudaStream_t st) {
     const int nb16 = (d->p + 15) / 16;
     if (nb16 > 4) return fail(ANML_EUNSUPPORTED, "fused path handles at most 64 columns");
     const long long nblk = (d->n + 31) / 32;
-    const bool specialised = (mode == 0) && hess && !m->no_specialise;
+    const bool specialised = hess && !m->no_specialise;
     int grid = (int)((nblk + (specialised ? 3 : 7)) / (specialised ? 4 : 8));
     if (grid > m->sm_count) grid = m->sm_count;
     if (grid < 1) grid = 1;
@@ -833,10 +864,11 @@ static int run_fused_block(anml_model* m, const anml_design* d, FusedArgs a, boo
     if (specialised) {
         const bool two = m->helpers == 2;
         const bool sgn = !weights_positive(a.family, a.link, a.fast != 0) || m->force_signed;
-#define HESS_CASE(NB)                                                                                         \
-    case NB:                                                                                                  \
-        if (two) rc = sgn ? launch_hess_t<NB, 2, true>(d, a, grid, st) : launch_hess_t<NB, 2, false>(d, a, grid, st); \
-        else rc = sgn ? launch_hess_t<NB, 1, true>(d, a, grid, st) : launch_hess_t<NB, 1, false>(d, a, grid, st);     \
+#define HESS_CASE(NB)                                                                                                  \
+    case NB:                                                                                                           \
+        if (mode == 1) rc = launch_hess_t<NB, 2, true, 1>(d, a, grid, st);                                             \
+        else if (two) rc = sgn ? launch_hess_t<NB, 2, true, 0>(d, a, grid, st) : launch_hess_t<NB, 2, false, 0>(d, a, grid, st); \
+        else rc = sgn ? launch_hess_t<NB, 1, true, 0>(d, a, grid, st) : launch_hess_t<NB, 1, false, 0>(d, a, grid, st);           \
         break;
         switch (nb16) {
             HESS_CASE(1)
@@ -952,7 +984,7 @@ static int eval_on_stream(anml_model* m, const double* x_host, int want, cudaStr
     const anml_design* d0 = m->par[0].design;
     if (m->K == 1 && d0->p <= 64 && !m->force_generic) {
         FusedArgs a;
-        a.n = m->n; a.p = d0->p; a.link = m->par[0].link; a.family = m->family; a.fast = (m->no_fast ? 0 : 1) | (m->debug_bits << 1);
+        a.n = m->n; a.p = d0->p; a.link = m->par[0].link; a.family = m->family; a.fast = m->no_fast ? 0 : 1;
         a.beta = m->d_beta + m->par[0].pad_off; a.obs = m->obs; a.se = m->se; a.offset = m->par[0].offset;
         a.rvec = nullptr; a.wvec = nullptr; a.partials = nullptr; a.status = nullptr;
         TRY(run_fused_block(m, d0, a, hess, 0, 0, 0, true, false, true, st));
@@ -980,22 +1012,27 @@ static int eval_general(anml_model* m, int want, cudaStream_t st) {
         TRY(ensure_vec(m, 5));
         TRY(ensure_vec(m, 6));
     }
-    for (int k = 0; k < K; ++k) {
-        TRY(launch_linpred(m->par[k].design, m->d_beta + m->par[k].off, m->par[k].offset, 0, -1, m->vec[k], m->d_status, st));
-        m->all_launches += 1;
+    const bool dual = (K == 2) && (m->par[0].design == m->par[1].design) && (m->par[0].design->p <= 64) && !m->force_generic;
+    if (dual) {
+        TRY(run_dual_terms(m, st));
+    } else {
+        for (int k = 0; k < K; ++k) {
+            TRY(launch_linpred(m->par[k].design, m->d_beta + m->par[k].off, m->par[k].offset, 0, -1, m->vec[k], m->d_status, st));
+            m->all_launches += 1;
+        }
+        RowTermsArgs ra;
+        ra.n = m->n; ra.family = m->family; ra.nparams = K; ra.link0 = m->par[0].link; ra.link1 = (K == 2) ? m->par[1].link : 0;
+        ra.fast = m->no_fast ? 0 : 1;
+        ra.y0 = m->vec[0]; ra.y1 = m->vec[1]; ra.obs = m->obs; ra.se = m->se;
+        ra.r0 = m->vec[2]; ra.r1 = m->vec[3]; ra.w00 = m->vec[4]; ra.w01 = m->vec[5]; ra.w11 = m->vec[6];
+        ra.obj_partials = m->d_partials; ra.status = m->d_status;
+        const int rgrid = grid_for(m->n, 256, m->sm_count, 8);
+        rowterms_kernel<<<rgrid, 256, 0, st>>>(ra);
+        CU_TRY(cudaGetLastError());
+        sum_partials_kernel<<<1, 256, 0, st>>>(m->d_partials, rgrid, m->d_packed, 0);
+        CU_TRY(cudaGetLastError());
+        m->all_launches += 2;
     }
-    RowTermsArgs ra;
-    ra.n = m->n; ra.family = m->family; ra.nparams = K; ra.link0 = m->par[0].link; ra.link1 = (K == 2) ? m->par[1].link : 0;
-    ra.fast = m->no_fast ? 0 : 1;
-    ra.y0 = m->vec[0]; ra.y1 = m->vec[1]; ra.obs = m->obs; ra.se = m->se;
-    ra.r0 = m->vec[2]; ra.r1 = m->vec[3]; ra.w00 = m->vec[4]; ra.w01 = m->vec[5]; ra.w11 = m->vec[6];
-    ra.obj_partials = m->d_partials; ra.status = m->d_status;
-    const int rgrid = grid_for(m->n, 256, m->sm_count, 8);
-    rowterms_kernel<<<rgrid, 256, 0, st>>>(ra);
-    CU_TRY(cudaGetLastError());
-    sum_partials_kernel<<<1, 256, 0, st>>>(m->d_partials, rgrid, m->d_packed, 0);
-    CU_TRY(cudaGetLastError());
-    m->all_launches += 2;
 
     for (int k = 0; k < K; ++k) {
         const anml_design* d = m->par[k].design;

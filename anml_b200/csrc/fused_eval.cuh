@@ -47,7 +47,41 @@ struct FusedArgs {
     const double* wvec;    // device (n)            [MODE 1]
     double* partials;      // [gridDim.x][EL]
     int* status;           // domain-violation flag
+    // MODE 2: two parameters over the same design (mean/variance model): second
+    // coefficient vector / link / offset, and the per-row vectors to write
+    const double* beta1;
+    const double* offset1;
+    int link1;
+    double *out_r0, *out_r1, *out_w00, *out_w01, *out_w11;
 };
+
+// 8 partial sums per lane -> one complete sum per lane: lane (g,t) keeps entry s == g,
+// summed over the 8 lanes that share t (3 shuffle stages, 7 exchanges).
+__device__ __forceinline__ double transpose_reduce8(const double* part, int g) {
+    double k4[4], k2[2];
+    {
+        const bool hi = (g & 4) != 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double send = hi ? part[q] : part[q + 4];
+            const double keep = hi ? part[q + 4] : part[q];
+            k4[q] = keep + shfl_xor_d(send, 16);
+        }
+    }
+    {
+        const bool hi = (g & 2) != 0;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const double send = hi ? k4[q] : k4[q + 2];
+            const double keep = hi ? k4[q + 2] : k4[q];
+            k2[q] = keep + shfl_xor_d(send, 8);
+        }
+    }
+    const bool hi = (g & 1) != 0;
+    const double send = hi ? k2[0] : k2[1];
+    const double keep = hi ? k2[1] : k2[0];
+    return keep + shfl_xor_d(send, 4);
+}
 
 template <int NB16>
 struct FusedCfg {
@@ -61,7 +95,7 @@ struct FusedCfg {
     static constexpr int RING_BYTES = NS * SLOT_BYTES;  // per warp
     static constexpr int EL_HESS = (2 * NT + NB8 + 1) * 32;  // doubles per CTA partial record
     static constexpr int EL_GRAD = (NB8 + 1) * 32;
-    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + WARPS * RING_BYTES + WARPS * NS * 8 + 16 * NB16 * 8;
+    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + WARPS * RING_BYTES + WARPS * NS * 8 + 2 * 16 * NB16 * 8;
 };
 
 template <int NB16, bool HESS, int MODE>
@@ -84,7 +118,10 @@ __global__ void __launch_bounds__(256, 1) fused_eval_kernel(const __grid_constan
         for (int i = 0; i < WARPS * NS; ++i) mbar_init(smem_u32(bars_all + i), 1);
         mbar_fence_init();
     }
-    if (threadIdx.x < 16 * NB16) beta_s[threadIdx.x] = (MODE == 0) ? a.beta[threadIdx.x] : 0.0;
+    if (threadIdx.x < 16 * NB16) {
+        beta_s[threadIdx.x] = (MODE == 0 || MODE == 2) ? a.beta[threadIdx.x] : 0.0;
+        beta_s[16 * NB16 + threadIdx.x] = (MODE == 2) ? a.beta1[threadIdx.x] : 0.0;
+    }
     __syncthreads();
 
     unsigned char* ring = ring_all + warp * C::RING_BYTES;
@@ -166,31 +203,7 @@ __global__ void __launch_bounds__(256, 1) fused_eval_kernel(const __grid_constan
                 part[s] = d;
             }
             // transposing reduction over the 8 lanes that share t: lane (g,t) keeps k-step s == g
-            double k4[4], k2[2], y;
-            {
-                const bool hi = (g & 4) != 0;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const double send = hi ? part[q] : part[q + 4];
-                    const double keep = hi ? part[q + 4] : part[q];
-                    k4[q] = keep + shfl_xor_d(send, 16);
-                }
-            }
-            {
-                const bool hi = (g & 2) != 0;
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const double send = hi ? k4[q] : k4[q + 2];
-                    const double keep = hi ? k4[q + 2] : k4[q];
-                    k2[q] = keep + shfl_xor_d(send, 8);
-                }
-            }
-            {
-                const bool hi = (g & 1) != 0;
-                const double send = hi ? k2[0] : k2[1];
-                const double keep = hi ? k2[1] : k2[0];
-                y = keep + shfl_xor_d(send, 4);
-            }
+            double y = transpose_reduce8(part, g);
             if (valid) {
                 if (a.offset) y += a.offset[row];
                 const double ob = a.obs[row];
@@ -201,6 +214,49 @@ __global__ void __launch_bounds__(256, 1) fused_eval_kernel(const __grid_constan
                 ww = rt.w;
                 bad_domain |= !rt.ok;
             }
+        } else if (MODE == 2) {
+            // ---- two linear predictors over the same rows (mean / variance model) ----
+            double part0[8], part1[8];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                const unsigned char* sp = (s < 4) ? sp0 : sp1;
+                const int ss = s & 3;
+                const int xr = 2 * t + (ss & 1);
+                const unsigned char* rp = sp + (xr + 8 * (ss >> 1)) * 128 + ((g ^ xr) << 4);
+                double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < NB16; ++j) {
+                    const double2 v = *reinterpret_cast<const double2*>(rp + j * 2048);
+                    const double2 b0 = *reinterpret_cast<const double2*>(beta_s + 16 * j + 2 * g);
+                    const double2 b1 = *reinterpret_cast<const double2*>(beta_s + 16 * NB16 + 16 * j + 2 * g);
+                    d0 = fma(v.x, b0.x, d0);
+                    d0 = fma(v.y, b0.y, d0);
+                    d1 = fma(v.x, b1.x, d1);
+                    d1 = fma(v.y, b1.y, d1);
+                }
+                part0[s] = d0;
+                part1[s] = d1;
+            }
+            double y0 = transpose_reduce8(part0, g);
+            double y1 = transpose_reduce8(part1, g);
+            if (valid) {
+                if (a.offset) y0 += a.offset[row];
+                if (a.offset1) y1 += a.offset1[row];
+                const RowTerms2 rt = row_terms2(a.link, a.link1, y0, y1, a.obs[row]);
+                objacc += rt.l;
+                a.out_r0[row] = rt.r0;
+                a.out_r1[row] = rt.r1;
+                a.out_w00[row] = rt.w00;
+                a.out_w01[row] = rt.w01;
+                a.out_w11[row] = rt.w11;
+                bad_domain |= !rt.ok;
+            }
+            // no gradient / Hessian here: both slots are consumed, re-arm them
+            __syncwarp();
+            if (lane == 0 && q_issue < nslots) issue_next();
+            if (lane == 0 && q_issue < nslots) issue_next();
+            ring_use = (s1 + 1 == NS) ? 0 : s1 + 1;
+            continue;
         } else {
             if (valid) {
                 rr = a.rvec[row];

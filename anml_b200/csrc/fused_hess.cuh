@@ -106,7 +106,9 @@ __device__ __forceinline__ void mma_kstep(double* acc, const double* av, uint32_
     }
 }
 
-template <int NB16, int NHELP, bool SIGNED>
+// MODE 0: per-row terms computed here from X, beta, obs (one-parameter models);
+// MODE 1: (r, w) read from a.rvec / a.wvec (blocks of the general path).
+template <int NB16, int NHELP, bool SIGNED, int MODE>
 __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const __grid_constant__ CUtensorMap tmap32, const FusedArgs a) {
     using C = HessCfg<NB16, NHELP>;
     constexpr int NB8 = C::NB8, NT = C::NT, NBUF = C::NBUF, TEAMS = C::TEAMS;
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
         for (int i = 0; i < TEAMS * NBUF * 2; ++i) mbar_init(bars_base + i * 8, 1);
         mbar_fence_init();
     }
-    if (threadIdx.x < 16 * NB16) sts64(beta_base + threadIdx.x * 8, a.beta[threadIdx.x]);
+    if (threadIdx.x < 16 * NB16) sts64(beta_base + threadIdx.x * 8, MODE == 0 ? a.beta[threadIdx.x] : 0.0);
     __syncthreads();
 
     const uint32_t ring_u32 = smem_base + team * C::TEAM_BYTES;
@@ -238,79 +240,52 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
             mbar_wait(full_u32 + buf * 8, (phase_bits >> buf) & 1u);
             phase_bits ^= 1u << buf;
             if ((int)(i % C::HELPERS) != hid) continue;
-            if (a.fast & 2) {  // DEBUG (option debug_skip_helpers): measure the tensor warp alone
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tbar_u32 + buf * 8);
-                continue;
-            }
             const long long row = (gp + i * GP) * 32 + R;
             const bool valid = row < a.n;
-            // per-row global loads first: their latency hides behind the dot products
-            double off = 0.0, ob = 0.0, se = 1.0;
-            if (valid) {
-                if (a.offset) off = a.offset[row];
-                ob = a.obs[row];
-                if (a.se) se = a.se[row];
-            }
-            const uint32_t bp = ring_u32 + buf * C::BUF_BYTES;
-            // ---- pass 1: linear predictor
-            double part[8];
-#pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                const int xr = 2 * t + (s & 1);
-                const int rowi = 16 * (s >> 2) + 8 * ((s >> 1) & 1) + xr;
-                const uint32_t rp = bp + rowi * 128 + ((g ^ xr) << 4);
-                double d = 0.0;
-#pragma unroll
-                for (int j = 0; j < NB16; ++j) {
-                    const double2 v = lds128(rp + j * 4096);
-                    d = fma(v.x, bsl[j].x, d);
-                    d = fma(v.y, bsl[j].y, d);
-                }
-                part[s] = d;
-            }
-            double k4[4], k2[2], y;
-            {
-                const bool hi = (g & 4) != 0;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const double send = hi ? part[q] : part[q + 4];
-                    const double keep = hi ? part[q + 4] : part[q];
-                    k4[q] = keep + shfl_xor_d(send, 16);
-                }
-            }
-            {
-                const bool hi = (g & 2) != 0;
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const double send = hi ? k4[q] : k4[q + 2];
-                    const double keep = hi ? k4[q + 2] : k4[q];
-                    k2[q] = keep + shfl_xor_d(send, 8);
-                }
-            }
-            {
-                const bool hi = (g & 1) != 0;
-                const double send = hi ? k2[0] : k2[1];
-                const double keep = hi ? k2[1] : k2[0];
-                y = keep + shfl_xor_d(send, 4);
-            }
             double rr = 0.0, ww = 0.0, sc = 0.0;
-            if (a.fast & 4) {  // DEBUG: no link/family math
-                rr = y * 1e-3;
-                ww = 0.25;
-                sc = 0.5;
+            const uint32_t bp = ring_u32 + buf * C::BUF_BYTES;
+            if (MODE == 0) {
+                // per-row global loads first: their latency hides behind the dot products
+                double off = 0.0, ob = 0.0, se = 1.0;
+                if (valid) {
+                    if (a.offset) off = a.offset[row];
+                    ob = a.obs[row];
+                    if (a.se) se = a.se[row];
+                }
+                // ---- pass 1: linear predictor
+                double part[8];
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const int xr = 2 * t + (s & 1);
+                    const int rowi = 16 * (s >> 2) + 8 * ((s >> 1) & 1) + xr;
+                    const uint32_t rp = bp + rowi * 128 + ((g ^ xr) << 4);
+                    double d = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NB16; ++j) {
+                        const double2 v = lds128(rp + j * 4096);
+                        d = fma(v.x, bsl[j].x, d);
+                        d = fma(v.y, bsl[j].y, d);
+                    }
+                    part[s] = d;
+                }
+                const double y = transpose_reduce8(part, g);
+                if (valid) {
+                    const RowTerms1 rt = row_terms1<true>(a.family, a.link, (a.fast & 1) != 0, y + off, ob, se);
+                    objacc += rt.l;
+                    rr = rt.r;
+                    ww = rt.w;
+                    sc = rt.sw;
+                    bad_domain |= !rt.ok;
+                }
             } else if (valid) {
-                const RowTerms1 rt = row_terms1<true>(a.family, a.link, (a.fast & 1) != 0, y + off, ob, se);
-                objacc += rt.l;
-                rr = rt.r;
-                ww = rt.w;
-                sc = rt.sw;
-                bad_domain |= !rt.ok;
+                rr = a.rvec[row];
+                ww = a.wvec[row];
+                sc = sqrt(fabs(ww));
             }
             if (SIGNED) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sign_u32 + buf * 128 + lane * 4), "r"(ww < 0.0 ? 0x80000000u : 0u) : "memory");
             // ---- pass 2: gradient, and rescale the block in place to sqrt(|w|) x
 #pragma unroll
-            for (int s = 0; s < 8 && !(a.fast & 8); ++s) {  // (fast & 8: DEBUG, skip pass 2)
+            for (int s = 0; s < 8; ++s) {
                 const int xr = 2 * t + (s & 1);
                 const int rowi = 16 * (s >> 2) + 8 * ((s >> 1) & 1) + xr;
                 const uint32_t rp = bp + rowi * 128 + ((g ^ xr) << 4);
