@@ -101,7 +101,6 @@ struct anml_model {
     double* se_owned = nullptr;
     bool prior_enabled = true;
     bool force_generic = false, no_fast = false, no_specialise = false;
-    int helpers = 2;
     bool force_signed = false;
     cudaStream_t stream = nullptr;
     int sm_count = 0;
@@ -695,7 +694,6 @@ extern "C" int anml_model_set_option(anml_model* m, const char* name, int64_t va
     if (!strcmp(name, "force_generic")) m->force_generic = value != 0;
     else if (!strcmp(name, "no_fast_math_paths")) m->no_fast = value != 0;
     else if (!strcmp(name, "no_warp_specialisation")) m->no_specialise = value != 0;
-    else if (!strcmp(name, "helpers")) m->helpers = (value == 1) ? 1 : 2;
     else if (!strcmp(name, "force_signed_weights")) m->force_signed = value != 0;
     else return fail(ANML_EINVAL, "unknown option '%s'", name);
     return ANML_OK;
@@ -862,13 +860,11 @@ static int run_fused_block(anml_model* m, const anml_design* d, FusedArgs a, boo
         else rc = hess ? launch_fused_t<NB, true, 1>(d, a, grid, st) : launch_fused_t<NB, false, 1>(d, a, grid, st);           \
         break;
     if (specialised) {
-        const bool two = m->helpers == 2;
         const bool sgn = !weights_positive(a.family, a.link, a.fast != 0) || m->force_signed;
-#define HESS_CASE(NB)                                                                                                  \
-    case NB:                                                                                                           \
-        if (mode == 1) rc = launch_hess_t<NB, 2, true, 1>(d, a, grid, st);                                             \
-        else if (two) rc = sgn ? launch_hess_t<NB, 2, true, 0>(d, a, grid, st) : launch_hess_t<NB, 2, false, 0>(d, a, grid, st); \
-        else rc = sgn ? launch_hess_t<NB, 1, true, 0>(d, a, grid, st) : launch_hess_t<NB, 1, false, 0>(d, a, grid, st);           \
+#define HESS_CASE(NB)                                                                              \
+    case NB:                                                                                       \
+        if (mode == 1) rc = launch_hess_t<NB, 2, true, 1>(d, a, grid, st);                         \
+        else rc = sgn ? launch_hess_t<NB, 2, true, 0>(d, a, grid, st) : launch_hess_t<NB, 2, false, 0>(d, a, grid, st); \
         break;
         switch (nb16) {
             HESS_CASE(1)

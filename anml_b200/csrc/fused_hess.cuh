@@ -47,7 +47,7 @@ struct HessCfg {
     static constexpr int HELPERS = NHELP;  // per team
     static constexpr int WARPS = TEAMS * (1 + HELPERS);
     static constexpr int THREADS = WARPS * 32;
-    // NHELP == 2: 384 threads x 168 regs = 4*32*216 + 8*32*144; NHELP == 1: 256 x 255, no transfer
+    // 384 threads x 168 registers at launch = 4*32*216 (tensor warps) + 8*32*144 (helpers)
     static constexpr int REGS_M = 216, REGS_H = 144;
     static constexpr int NB8 = 2 * NB16;
     static constexpr int NT = NB8 * (NB8 + 1) / 2;
@@ -55,7 +55,7 @@ struct HessCfg {
     static constexpr int NBUF = (49152 / BUF_BYTES) > 8 ? 8 : (49152 / BUF_BYTES);
     static constexpr int TEAM_BYTES = NBUF * BUF_BYTES;
     static constexpr int EL = (2 * NT + NB8 + 1) * 32;
-    static constexpr int SMEM_BYTES = 1024 + TEAMS * TEAM_BYTES + TEAMS * NBUF * 32 * 4 /*sign masks*/ + TEAMS * NBUF * 2 * 8 /*bars*/ +
+    static constexpr int SMEM_BYTES = 1024 + TEAMS * TEAM_BYTES + TEAMS * NBUF * 32 * 4 /*sign masks*/ + TEAMS * NBUF * 2 * 8 /*full barriers, ready flags*/ +
                                       16 * NB16 * 8 /*beta*/ + TEAMS * HELPERS * (NB8 + 1) * 32 * 8 /*helper g, obj*/;
 };
 
@@ -66,6 +66,12 @@ __device__ __forceinline__ void dmma884_nv(double& c0, double& c1, double a, dou
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// flag read used for synchronisation: "memory" keeps the compiler from caching or dropping it
+__device__ __forceinline__ uint32_t lds32_sync(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
 __device__ __forceinline__ void sts128(uint32_t addr, double x, double y) {
@@ -129,7 +135,11 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap32);
-        for (int i = 0; i < TEAMS * NBUF * 2; ++i) mbar_init(bars_base + i * 8, 1);
+        for (int q = 0; q < TEAMS; ++q)
+            for (int i = 0; i < NBUF; ++i) {
+                mbar_init(bars_base + (q * NBUF * 2 + i) * 8, 1);
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(bars_base + (q * NBUF * 2 + NBUF + i) * 8), "r"(0) : "memory");
+            }
         mbar_fence_init();
     }
     if (threadIdx.x < 16 * NB16) sts64(beta_base + threadIdx.x * 8, MODE == 0 ? a.beta[threadIdx.x] : 0.0);
@@ -138,7 +148,7 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
     const uint32_t ring_u32 = smem_base + team * C::TEAM_BYTES;
     const uint32_t sign_u32 = signs_base + team * NBUF * 32 * 4;        // [buf][32] sign bit of w per row
     const uint32_t full_u32 = bars_base + team * NBUF * 2 * 8;          // full[b]  : TMA bytes landed
-    const uint32_t tbar_u32 = full_u32 + NBUF * 8;                      // terms[b] : block rescaled, signs published
+    const uint32_t rdy_u32 = full_u32 + NBUF * 8;                       // ready[b] : u32 sequence flag, block rescaled + signs published
 
     const long long nblk = (a.n + 31) >> 5;
     const long long gp = (long long)blockIdx.x * TEAMS + team;
@@ -173,26 +183,32 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
         uint32_t sgA = 0, sgB = 0;
         uint32_t phase_bits = 0;
         int buf = 0;
+        // The helpers publish "block i is rescaled" as a sequence number in shared memory
+        // (ready[b] = i + 1).  The tensor warp must never execute a long-latency dependent
+        // instruction (a stall longer than one DMMA is a pipe bubble), so it reads the flag
+        // with a plain LDS two k-steps ahead, like a fragment, instead of an mbarrier wait.
         if (nmine > 0) {
-            mbar_wait(tbar_u32, 0);
-            load_kstep<NB16>(avA, ring_u32, 0, g, t);
-            if (SIGNED) sgA = lds32(sign_u32 + t * 4);
+            uint32_t f0;
+            do { f0 = lds32_sync(rdy_u32); } while (f0 != 1u);
+            // (f0 ^ 1) == 0: an address dependency, so no fragment load can be issued before the flag arrived
+            load_kstep<NB16>(avA, ring_u32 + (f0 ^ 1u), 0, g, t);
+            if (SIGNED) sgA = lds32(sign_u32 + (f0 ^ 1u) + t * 4);
         }
         for (long long i = 0; i < nmine; ++i) {
             phase_bits ^= 1u << buf;
             const uint32_t bp = ring_u32 + buf * C::BUF_BYTES;
             const uint32_t sb = sign_u32 + buf * 128;
             const int nbuf = (buf + 1 == NBUF) ? 0 : buf + 1;
-            const uint32_t npar = (phase_bits >> nbuf) & 1u;
             const bool has_next = i + 1 < nmine;
-            bool nready = false;
+            const uint32_t want_flag = (uint32_t)(i + 2);  // block i+1 published
+            uint32_t seen_flag = 0;
 #pragma unroll
             for (int s = 0; s < 8; s += 2) {
                 // even k-step on set A, prefetch k-step s+1 into set B
                 load_kstep<NB16>(avB, bp, s + 1, g, t);
                 if (SIGNED) sgB = lds32(sb + (4 * (s + 1) + t) * 4);
                 mma_kstep<NB8, SIGNED>(acc, avA, sgA);
-                if (s == 4 && has_next) nready = mbar_try(tbar_u32 + nbuf * 8, npar);  // answer returns behind DMMAs
+                if (s == 4) seen_flag = lds32_sync(rdy_u32 + nbuf * 8);  // consumed two k-steps later
                 // odd k-step on set B, prefetch k-step s+2 (or the next block's first) into set A
                 if (s + 2 < 8) {
                     load_kstep<NB16>(avA, bp, s + 2, g, t);
@@ -204,10 +220,16 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // helper's in-place stores before the refill
                         issue(i + NBUF, buf);
                     }
-                    if (has_next && !nready) mbar_wait(tbar_u32 + nbuf * 8, npar);
-                    // (without a next block this reads stale but valid shared memory; the values are never used)
-                    load_kstep<NB16>(avA, ring_u32 + nbuf * C::BUF_BYTES, 0, g, t);
-                    if (SIGNED) sgA = lds32(sign_u32 + nbuf * 128 + t * 4);
+                    if (has_next) {
+                        while (seen_flag != want_flag) seen_flag = lds32_sync(rdy_u32 + nbuf * 8);
+                    } else {
+                        seen_flag = want_flag;
+                    }
+                    // (seen ^ want) == 0: address dependency on the flag (see prologue).  Without a next
+                    // block this reads stale but valid shared memory; the values are never used.
+                    const uint32_t dep = seen_flag ^ want_flag;
+                    load_kstep<NB16>(avA, ring_u32 + nbuf * C::BUF_BYTES + dep, 0, g, t);
+                    if (SIGNED) sgA = lds32(sign_u32 + nbuf * 128 + dep + t * 4);
                 }
                 mma_kstep<NB8, SIGNED>(acc, avB, sgB);
             }
@@ -300,7 +322,10 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(tbar_u32 + buf * 8);
+            if (lane == 0) {
+                __threadfence_block();  // the block's stores before the flag
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(rdy_u32 + buf * 8), "r"((uint32_t)(i + 1)) : "memory");
+            }
         }
         if (bad_domain) atomicOr(a.status, 1);
         {

@@ -92,20 +92,19 @@ def test_symmetric_warp_kernel_variant(p):
 
 
 @pytest.mark.parametrize("p", [4, 40, 64])
-@pytest.mark.parametrize("helpers", [1, 2])
-def test_signed_weight_path_and_helper_count(p, helpers):
+def test_signed_weight_path(p):
     """The tensor warp multiplies sqrt(|w|) x fragments; rows with w < 0 flip the B
     operand's sign bit.  Force that path on a canonical model (all w > 0) and run a
     non-canonical one (gaussian + exp link: w changes sign with the residual)."""
     X, obs, se, off, link, x = make_problem("binomial", 6007, p, seed=p + 7, with_offset=True)
     want = O.model_eval_fused("binomial", obs, [X], [link], x, offsets=[off])
-    check(gpu_eval("binomial", X, obs, se, off, link, x, options=(("force_signed_weights", 1), ("helpers", helpers))), want)
+    check(gpu_eval("binomial", X, obs, se, off, link, x, options=(("force_signed_weights", 1),)), want)
     X, obs, se, off, link, x = make_problem("gaussian", 6007, p, seed=p + 9, link="exp")
     obs = obs + 2.0 * np.random.default_rng(p).normal(size=obs.size)  # large residuals -> negative weights
     want = O.model_eval_fused("gaussian", obs, [X], ["exp"], x)
     w_neg = ((np.exp(X @ x) - obs) * np.exp(X @ x) + np.exp(2 * (X @ x)) < 0).mean()
     assert 0.02 < w_neg < 0.98
-    check(gpu_eval("gaussian", X, obs, None, None, "exp", x, options=(("helpers", helpers),)), want)
+    check(gpu_eval("gaussian", X, obs, None, None, "exp", x), want)
 
 
 def test_general_path_matches_fused():
