@@ -1,0 +1,136 @@
+"""Parity at BASELINE.json's full single-GPU sizes, through checks that do not
+need the CPU oracle to hold the data: an independent FP64 evaluation with
+torch/cuBLAS on the same device-resident inputs, shard additivity, determinism,
+and (splines) partition of unity + interval indices against torch.searchsorted.
+Inputs are generated on the device (torch), as bench.py does."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SEED = 20261019
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("needs CUDA")
+    return torch
+
+
+def make_logistic(torch, n, p, seed):
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    beta_true = torch.randn(p, dtype=torch.float64, device=dev, generator=g) * 0.1
+    X = torch.empty((n, p), dtype=torch.float64, device=dev)
+    obs = torch.empty(n, dtype=torch.float64, device=dev)
+    chunk = 1 << 21
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        X[lo:hi].normal_(generator=g)
+        X[lo:hi, 0] = 1.0
+        obs[lo:hi] = (torch.rand(hi - lo, dtype=torch.float64, device=dev, generator=g) < torch.sigmoid(X[lo:hi] @ beta_true)).double()
+    return X, obs, beta_true
+
+
+def native_model(X, obs, lo, hi, prior=True):
+    from anml_b200 import _native as N
+
+    n, p = hi - lo, X.shape[1]
+    Xs = X[lo:hi]
+    d = N.Design.wrap(Xs.data_ptr(), n, p, p, keepalive=Xs)
+    m = N.NativeModel(n, "binomial", 1)
+    m.set_param(0, d, N.LINK_CODES["Expit"])
+    os_ = obs[lo:hi]
+    m.set_obs(dev_ptr=os_.data_ptr(), keepalive=os_)
+    if prior:
+        m.set_gaussian_prior(0, np.zeros(p), np.ones(p))
+    return m
+
+
+def test_config2_logistic_10m_rows_against_torch_fp64():
+    """BASELINE config #2: binomial/expit, 1e7 rows x 64, GaussianPrior(0,1)."""
+    torch = _torch()
+    n, p = 10_000_000, 64
+    X, obs, beta_true = make_logistic(torch, n, p, SEED + 2)
+    x = (0.5 * beta_true).cpu().numpy()
+    model = native_model(X, obs, 0, n)
+    o, g, H = model.eval(x)
+    o2, g2, H2 = model.eval(x)
+    assert o == o2 and np.array_equal(g, g2) and np.array_equal(H, H2)  # bitwise reproducible
+    assert np.array_equal(H, H.T)
+
+    # independent evaluation: torch FP64 (cuBLAS DGEMV/DGEMM), chunked
+    xb = torch.from_numpy(x).cuda()
+    obj = torch.zeros((), dtype=torch.float64, device="cuda")
+    grad = torch.zeros(p, dtype=torch.float64, device="cuda")
+    hess = torch.zeros((p, p), dtype=torch.float64, device="cuda")
+    chunk = 1 << 21
+    for lo in range(0, n, chunk):
+        Xc, oc = X[lo:lo + chunk], obs[lo:lo + chunk]
+        y = Xc @ xb
+        th = torch.sigmoid(y)
+        obj += -(oc * torch.log(th) + (1 - oc) * torch.log1p(-th)).sum()
+        grad += Xc.t() @ (th - oc)
+        hess += (Xc.t() * (th * (1 - th))) @ Xc
+    obj += 0.5 * (xb**2).sum()
+    grad += xb
+    hess += torch.eye(p, dtype=torch.float64, device="cuda")
+    ow, gw, Hw = float(obj), grad.cpu().numpy(), hess.cpu().numpy()
+    assert abs(o - ow) <= 1e-10 * abs(ow)
+    assert np.abs(g - gw).max() <= 1e-10 * np.abs(gw).max()
+    assert np.abs(H - Hw).max() <= 1e-9 * np.abs(Hw).max()
+
+    # shard additivity (what the multi-GPU path relies on): halves sum to the whole
+    a = native_model(X, obs, 0, n // 2 + 7, prior=True)   # "rank 0" carries the prior
+    b = native_model(X, obs, n // 2 + 7, n, prior=False)
+    oa, ga, Ha = a.eval(x)
+    ob, gb, Hb = b.eval(x)
+    assert abs((oa + ob) - o) <= 1e-12 * abs(o)
+    assert np.abs(ga + gb - g).max() <= 1e-12 * np.abs(g).max()
+    assert np.abs(Ha + Hb - H).max() <= 1e-12 * np.abs(H).max()
+
+    # gradient pass alone (no Hessian) returns the same objective and gradient
+    from anml_b200 import _native as N
+    o3, g3, _ = model.eval(x, N.WANT_OBJ | N.WANT_GRAD)
+    assert abs(o3 - o) <= 1e-13 * abs(o) and np.abs(g3 - g).max() <= 1e-12 * np.abs(g).max()
+
+
+def test_config3_spline_50m_rows_partition_of_unity_and_indices():
+    """BASELINE config #3: 5e7 rows, 20 knots, degree 3 -> 22 bases built on the device."""
+    torch = _torch()
+    from anml_b200 import _native as N
+
+    n, nk, deg = 50_000_000, 20, 3
+    g = torch.Generator(device="cuda")
+    g.manual_seed(SEED + 3)
+    xs = torch.rand(n, dtype=torch.float64, device="cuda", generator=g)
+    knots = np.linspace(0.0, 1.0, nk)
+    xs[:nk] = torch.from_numpy(knots).cuda()  # exact knots and both end points
+    nb = nk - 1 + deg
+    design = N.Design(n, nb)
+    idx = design.set_spline(0, None, knots, deg, want_index=True, x_dev_ptr=xs.data_ptr())
+    want_idx = torch.clamp(torch.searchsorted(torch.from_numpy(knots).cuda(), xs, right=True) - 1, 0, nk - 2).cpu().numpy()
+    np.testing.assert_array_equal(idx, want_idx.astype(np.int32))
+    # partition of unity: design @ 1 == 1 for every row (get_params order 0, identity)
+    ones = design.params(np.ones(nb), None, N.LINK_CODES["Identity"], 0)
+    assert np.abs(ones - 1.0).max() <= 4e-16 * 4
+    # 4 non-zeros per row, located at the interval: column sums of |basis| outside [idx, idx+3] are zero
+    import ctypes as C
+    n_rows, n_cols, ld, ptr = C.c_int64(), C.c_int(), C.c_int64(), C.c_void_p()
+    N.check(N.load().anml_design_shape(design.handle, C.byref(n_rows), C.byref(n_cols), C.byref(ld), C.byref(ptr)))
+    assert (n_rows.value, n_cols.value, ld.value) == (n, nb, nb)
+    # Gaussian model on the spline design: Hessian is banded (bandwidth degree) and independent of x
+    obs = torch.sin(2 * np.pi * xs) + 0.1 * torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    m = N.NativeModel(n, "gaussian", 1)
+    m.set_param(0, design, N.LINK_CODES["Identity"])
+    m.set_obs(dev_ptr=obs.data_ptr(), keepalive=obs)
+    o0, g0, H0 = m.eval(np.zeros(nb))
+    o1, g1, H1 = m.eval(np.linspace(-1, 1, nb))
+    assert np.array_equal(H0, H1)
+    i, j = np.indices(H0.shape)
+    assert np.all(H0[np.abs(i - j) > deg] == 0.0) and np.all(np.diag(H0) > 0)
+    assert abs(H0.sum() - n) <= 1e-10 * n  # sum_ij H_ij = sum_rows (sum_j B_j)^2 = n
+    assert abs(o0 - 0.5 * float((obs**2).sum())) <= 1e-12 * o0
