@@ -67,6 +67,8 @@ struct anml_design {
     bool owned = false;
     CUtensorMap tmap;    // box 16 rows x 16 cols, 128B swizzle
     CUtensorMap tmap32;  // box 32 rows x 16 cols, 128B swizzle
+    double* stage = nullptr;  // upload staging buffer, kept between set_columns calls
+    long long stage_elems = 0;
     int sm_count = 0;
 };
 
@@ -280,6 +282,7 @@ extern "C" int anml_design_destroy(anml_design* d) {
     if (!d) return ANML_OK;
     cudaSetDevice(d->device);
     if (d->owned && d->X) cudaFree(d->X);
+    if (d->stage) cudaFree(d->stage);
     delete d;
     return ANML_OK;
 }
@@ -312,29 +315,40 @@ extern "C" int anml_design_set_columns(anml_design* d, int col0, int ncols, cons
         CU_TRY(cudaDeviceSynchronize());
         return ANML_OK;
     }
-    // host source: stage through a bounded dense device buffer, chunk of rows at a time
+    // host source: stage through a bounded dense device buffer (kept in the handle), chunk of rows at a time
     const long long max_elems = 1LL << 25;  // 256 MiB of doubles
     long long rows_per_chunk = max_elems / ncols;
     if (rows_per_chunk < 1) rows_per_chunk = 1;
     if (rows_per_chunk > d->n) rows_per_chunk = d->n;
-    double* tmp = nullptr;
-    CU_TRY(cudaMalloc(&tmp, (size_t)rows_per_chunk * ncols * sizeof(double)));
+    if (d->stage_elems < rows_per_chunk * ncols) {
+        if (d->stage) CU_TRY(cudaFree(d->stage));
+        d->stage = nullptr;
+        d->stage_elems = 0;
+        CU_TRY(cudaMalloc(&d->stage, (size_t)rows_per_chunk * ncols * sizeof(double)));
+        d->stage_elems = rows_per_chunk * ncols;
+    }
+    double* tmp = d->stage;
     for (long long r0 = 0; r0 < d->n; r0 += rows_per_chunk) {
         const long long rows = (d->n - r0 < rows_per_chunk) ? d->n - r0 : rows_per_chunk;
-        cudaError_t e = cudaMemcpy2D(tmp, (size_t)ncols * sizeof(double), src + r0 * src_ld, (size_t)src_ld * sizeof(double),
-                                     (size_t)ncols * sizeof(double), (size_t)rows, cudaMemcpyHostToDevice);
+        cudaError_t e;
+        if (src_ld == ncols)  // dense block: one linear copy
+            e = cudaMemcpyAsync(tmp, src + r0 * src_ld, (size_t)rows * ncols * sizeof(double), cudaMemcpyHostToDevice, 0);
+        else
+            e = cudaMemcpy2DAsync(tmp, (size_t)ncols * sizeof(double), src + r0 * src_ld, (size_t)src_ld * sizeof(double),
+                                  (size_t)ncols * sizeof(double), (size_t)rows, cudaMemcpyHostToDevice, 0);
         if (e == cudaSuccess) {
             scatter_columns_kernel<<<grid_for(rows * ncols, 256, d->sm_count), 256>>>(d->X + r0 * d->ld, rows, d->ld, col0, ncols, tmp, ncols);
             e = cudaGetLastError();
         }
-        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        // the next chunk reuses the staging buffer: wait for the scatter (stream order also covers it,
+        // the explicit sync keeps error reporting local)
+        if (e == cudaSuccess && r0 + rows_per_chunk < d->n) e = cudaStreamSynchronize(0);
         if (e != cudaSuccess) {
-            cudaFree(tmp);
             (void)cudaGetLastError();
             return fail(ANML_ECUDA, "anml_design_set_columns: %s", cudaGetErrorString(e));
         }
     }
-    CU_TRY(cudaFree(tmp));
+    CU_TRY(cudaStreamSynchronize(0));
     return ANML_OK;
 }
 
@@ -831,7 +845,7 @@ static int run_dual_terms(anml_model* m, cudaStream_t st) {
     }
     TRY(rc);
     const int el = fused_el(nb16, false);
-    reduce_partials_kernel<<<(el + 255) / 256, 256, 0, st>>>(m->d_partials, grid, el, m->d_reduced);
+    reduce_partials_kernel<<<(el + 127) / 128, 128, 0, st>>>(m->d_partials, grid, el, m->d_reduced);
     CU_TRY(cudaGetLastError());
     assemble_kernel<<<1, 256, 0, st>>>(m->d_reduced, nb16, 0, d->p, m->d_packed, m->P, 0, 0, 0, 0);  // objective only
     CU_TRY(cudaGetLastError());
@@ -884,7 +898,7 @@ static int run_fused_block(anml_model* m, const anml_design* d, FusedArgs a, boo
     TRY(rc);
     if (ep) CU_TRY(cudaEventRecord(ep->b, st));
     const int el = fused_el(nb16, hess);
-    reduce_partials_kernel<<<(el + 255) / 256, 256, 0, st>>>(m->d_partials, grid, el, m->d_reduced);
+    reduce_partials_kernel<<<(el + 127) / 128, 128, 0, st>>>(m->d_partials, grid, el, m->d_reduced);
     CU_TRY(cudaGetLastError());
     assemble_kernel<<<1, 256, 0, st>>>(m->d_reduced, nb16, hess ? 1 : 0, d->p, m->d_packed, m->P, row_off, col_off,
                                        write_grad ? 1 : 0, add_obj ? 1 : 0);

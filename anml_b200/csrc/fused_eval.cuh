@@ -330,20 +330,28 @@ __global__ void __launch_bounds__(256, 1) fused_eval_kernel(const __grid_constan
 }
 
 // Sum the per-CTA partial records in a fixed order: reduced[e] = sum_c partials[c][e].
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partials, int ncta, int el,
+// 16 independent loads in flight per thread (the loop is latency-bound: 148 records,
+// 2.6k elements), combined in a fixed tree so the result does not depend on timing.
+__global__ void __launch_bounds__(128) reduce_partials_kernel(const double* __restrict__ partials, int ncta, int el,
                                                               double* __restrict__ reduced) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= el) return;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    double s[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) s[u] = 0.0;
     int c = 0;
-    for (; c + 3 < ncta; c += 4) {
-        s0 += partials[(size_t)c * el + e];
-        s1 += partials[(size_t)(c + 1) * el + e];
-        s2 += partials[(size_t)(c + 2) * el + e];
-        s3 += partials[(size_t)(c + 3) * el + e];
+    for (; c + 15 < ncta; c += 16) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) s[u] += partials[(size_t)(c + u) * el + e];
     }
-    for (; c < ncta; ++c) s0 += partials[(size_t)c * el + e];
-    reduced[e] = (s0 + s1) + (s2 + s3);
+    double tail = 0.0;
+    for (; c < ncta; ++c) tail += partials[(size_t)c * el + e];
+    s[0] += tail;
+#pragma unroll
+    for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+        for (int u = 0; u < w; ++u) s[u] += s[u + w];
+    reduced[e] = s[0];
 }
 
 // Undo the fragment/tile layout into the packed record

@@ -80,6 +80,9 @@ class ShardedModel:
         self._cache = None
         self.num_evaluations = 0
         self._cmd = None
+        self._cmd_host = None
+        self._packed_host = None
+        self._on_gpu = hasattr(local, "packed") and local.packed.is_cuda
 
     # ---- collective evaluation (every rank calls this with the same x) -------------
     def evaluate_collective(self, x: np.ndarray, hessian: bool = True):
@@ -93,7 +96,18 @@ class ShardedModel:
 
     def unpack(self, packed, hessian: bool = True):
         P = self.P
-        host = packed.detach().cpu().numpy() if hasattr(packed, "detach") else np.asarray(packed)
+        if hasattr(packed, "detach"):
+            if packed.is_cuda:
+                # pinned staging buffer + one stream sync instead of a pageable blocking copy
+                if self._packed_host is None:
+                    self._packed_host = self.torch.empty(packed.numel(), dtype=packed.dtype, pin_memory=True)
+                self._packed_host.copy_(packed.detach(), non_blocking=True)
+                self.torch.cuda.current_stream(packed.device).synchronize()
+                host = self._packed_host.numpy()
+            else:
+                host = packed.detach().numpy()
+        else:
+            host = np.asarray(packed)
         if host[1 + P + P * P] != 0.0:
             raise ValueError("linear predictor outside the domain of a Log/Logit mapping")
         obj = float(host[0])
@@ -103,20 +117,27 @@ class ShardedModel:
 
     # ---- rank-0 driver / worker loop ---------------------------------------------------
     def _command(self, op: float, x: Optional[np.ndarray]):
+        """Rank 0 broadcasts [op | x]; every rank returns (op, x).  Rank 0 does not read the
+        broadcast back, the others do one pinned device-to-host copy."""
         torch = self.torch
         if self.world == 1:
             return op, x
         dev = self.local.packed.device if hasattr(self.local, "packed") else torch.device("cpu")
         if self._cmd is None:
             self._cmd = torch.zeros(1 + self.P, dtype=torch.float64, device=dev)
+            self._cmd_host = torch.zeros(1 + self.P, dtype=torch.float64, pin_memory=self._on_gpu)
         if self.rank == 0:
-            buf = np.zeros(1 + self.P)
+            buf = self._cmd_host.numpy()
             buf[0] = op
-            if x is not None:
-                buf[1:] = x
-            self._cmd.copy_(torch.from_numpy(buf))
+            buf[1:] = 0.0 if x is None else x
+            self._cmd.copy_(self._cmd_host, non_blocking=True)
+            self.dist.broadcast(self._cmd, src=0, group=self.group)
+            return op, (None if x is None else np.array(x, dtype=np.float64, copy=True))
         self.dist.broadcast(self._cmd, src=0, group=self.group)
-        host = self._cmd.cpu().numpy()
+        self._cmd_host.copy_(self._cmd, non_blocking=True)
+        if self._on_gpu:
+            torch.cuda.current_stream(dev).synchronize()
+        host = self._cmd_host.numpy()
         return float(host[0]), host[1:].copy()
 
     def evaluate(self, x, hessian: bool = True):
