@@ -933,16 +933,32 @@ static EventPair* next_events(anml_model* m);
 // or two different designs (wide_hessian.cuh).
 static int run_wide_hessian(anml_model* m, const anml_design* da, const anml_design* db, const double* w, int row_off, int col_off,
                             cudaStream_t st) {
-    const int nba = (da->p + 127) / 128, nbb = (db->p + 127) / 128;
+    const int nba = (da->p + 127) / 128, nbb = (db->p + 63) / 64;  // 128-column blocks of Xa, 64-column blocks of Xb
     const bool symmetric = (da == db) && (row_off == col_off);
-    const int npairs = symmetric ? nba * (nba + 1) / 2 : nba * nbb;
-    long long S = (2LL * m->sm_count + npairs - 1) / npairs;
-    if (S < 1) S = 1;
+    // symmetric: row bi of the block grid holds the 2*bi+2 blocks that touch or lie below the diagonal
+    const int npairs = symmetric ? nba * (nba + 1) : nba * nbb;
+    // Row chunks: about 12 waves of CTAs (the hardware scheduler then balances diagonal blocks, which do
+    // less work), with the count nudged so that the last wave is as full as possible; at least 1024 rows each.
+    long long S0 = (12LL * m->sm_count + npairs - 1) / npairs;
+    const long long s_max = (m->n_pad + 1023) / 1024;
+    if (S0 > s_max) S0 = s_max;
+    if (S0 < 1) S0 = 1;
+    long long S = S0;
+    double best_fill = -1.0;
+    for (long long c = (S0 > 3 ? S0 - 3 : 1); c <= S0 + 3 && c <= (s_max > 1 ? s_max : 1); ++c) {
+        const long long ctas = c * npairs;
+        const long long waves = (ctas + m->sm_count - 1) / m->sm_count;
+        const double fill = (double)ctas / (double)(waves * m->sm_count);
+        if (fill > best_fill + 1e-9) {
+            best_fill = fill;
+            S = c;
+        }
+    }
     long long chunk_rows = (m->n_pad + S - 1) / S;
     chunk_rows = round_up_ll(chunk_rows, 16);
     if (chunk_rows < 16) chunk_rows = 16;
     S = (m->n_pad + chunk_rows - 1) / chunk_rows;
-    const long long need = S * npairs * 16384LL;
+    const long long need = S * npairs * (long long)WIDE_TILE_ELEMS;
     if (need > m->wide_len) {
         CU_TRY(cudaStreamSynchronize(st));
         if (m->d_wide) CU_TRY(cudaFree(m->d_wide));
@@ -964,7 +980,7 @@ static int run_wide_hessian(anml_model* m, const anml_design* da, const anml_des
     wide_hessian_kernel<<<(unsigned)(S * npairs), WIDE_THREADS, WIDE_SMEM_BYTES, st>>>(da->tmap, db->tmap, a);
     CU_TRY(cudaGetLastError());
     if (ep) CU_TRY(cudaEventRecord(ep->b, st));
-    const long long total = (long long)npairs * 16384;
+    const long long total = (long long)npairs * WIDE_TILE_ELEMS;
     wide_reduce_kernel<<<grid_for(total, 256, m->sm_count, 8), 256, 0, st>>>(m->d_wide, (int)S, npairs, nbb, symmetric ? 1 : 0, da->p, db->p,
                                                                             m->d_packed + 1 + m->P, m->P, row_off, col_off);
     CU_TRY(cudaGetLastError());
