@@ -41,8 +41,8 @@ N_TOTAL = 100_000_000
 P = 64
 METRIC = "obj+grad+Hessian evals/sec at N=100M,p=64"
 UNIT = "evals/s"
-# dram bytes per row of the fused kernel from the ncu --set full capture in profiles/ (n = 1e7: 5.2035 GB)
-NCU_DRAM_BYTES_PER_ROW = 520.35
+# dram bytes per row of the fused kernel from the ncu --set full capture in profiles/ (n = 1e7: 5.2136 GB, profiles/r1_fused_hess_kernel_ncu.csv)
+NCU_DRAM_BYTES_PER_ROW = 521.36
 
 
 def workload_name(n_total, p):
