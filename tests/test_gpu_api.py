@@ -211,3 +211,35 @@ def test_spline_variable_in_a_parameter_and_smoothing_prior():
     assert np.abs(model.gradient(res.x)).max() < 1e-5  # a stationary point of the penalised likelihood
     fitted = D @ res.x
     assert np.sqrt(np.mean((fitted - np.sin(2 * np.pi * xs)) ** 2)) < 0.05
+
+
+def test_sharded_model_single_rank_uses_the_async_device_path(golden):
+    """ShardedModel + NativeLocalEvaluator on one rank: eval_async into a torch CUDA
+    tensor on torch's current stream, pinned read-back, solver loop."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("needs CUDA")
+    from anml_b200.data import DataExample
+    from anml_b200.distributed import NativeLocalEvaluator, ShardedModel
+    from anml_b200.model import Model
+    from anml_b200.prior import GaussianPrior
+
+    case = "binom_p64"
+    X = golden[f"model/{case}/X"]
+    extra = {"obs": golden[f"model/{case}/obs"], "se": golden[f"model/{case}/se"]}
+    par = make_parameter(X.shape[1], "expit", var_priors=[GaussianPrior(mean=0.0, sd=1.0)])
+    model = Model("binomial", DataExample("obs", "se"), [par])
+    model.attach(frame_from(X, extra))
+    sharded = ShardedModel(NativeLocalEvaluator(model))
+    x = golden[f"model/{case}/x"]
+    with torch.cuda.stream(torch.cuda.Stream()):  # a non-default torch stream
+        o, g, H = sharded.evaluate(x)
+    o2, g2, H2 = sharded.evaluate(x * 1.0)  # cache hit on equal bytes
+    assert sharded.num_evaluations == 1 and o2 == o
+    assert abs(o - float(golden[f"model/{case}/obj"])) <= 1e-10 * abs(o)
+    assert np.abs(g - golden[f"model/{case}/grad"]).max() <= 1e-10 * np.abs(g).max()
+    assert np.abs(H - golden[f"model/{case}/hess"]).max() <= 1e-9 * np.abs(H).max()
+    direct = model.evaluate(x)
+    assert direct[0] == o and np.array_equal(direct[1], g) and np.array_equal(direct[2], H)
+    res = sharded.fit(np.zeros(x.size), options={"gtol": 1e-8, "maxiter": 50})
+    assert np.abs(sharded.gradient(res.x)).max() < 1e-6
