@@ -376,7 +376,27 @@ static int run_spline(int device, int sm_count, const double* x_dev, long long n
         SplineArgs a;
         a.x = x_dev; a.n = n; a.t = t_dev; a.nk = nk; a.degree = degree; a.ldegree = ldegree; a.rdegree = rdegree;
         a.order = order; a.out = out_dev; a.ld = ld; a.col0 = col0; a.idx_out = idx_dev;
-        spline_design_kernel<<<grid_for(n, 256, sm_count), 256, nt * sizeof(double)>>>(a);
+        const int nb = nk - 1 + degree;
+        const size_t smem = ((size_t)((nt + 1) & ~1) + (size_t)256 * (nb + 1)) * sizeof(double);
+        if (smem > 200 * 1024) {
+            cudaFree(t_dev);
+            return fail(ANML_EUNSUPPORTED, "spline with %d basis functions needs %zu bytes of shared memory per block", nb, smem);
+        }
+        const int grid = grid_for(n, 256, sm_count, 4);
+#define SPLINE_CASE(D)                                                                                                   \
+    case D:                                                                                                              \
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(spline_design_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e == cudaSuccess) spline_design_kernel<D><<<grid, 256, smem>>>(a);                                           \
+        break;
+        switch (degree) {
+            SPLINE_CASE(0)
+            SPLINE_CASE(1)
+            SPLINE_CASE(2)
+            SPLINE_CASE(3)
+            SPLINE_CASE(4)
+            SPLINE_CASE(5)
+        }
+#undef SPLINE_CASE
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
     }
