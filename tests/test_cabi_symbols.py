@@ -55,3 +55,23 @@ def test_no_cpu_fallback_when_no_device():
         _native.Design(10, 2)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _native.spline_design([0.5], [0.0, 1.0], 3)
+
+
+def test_plain_c_program_links_and_runs(tmp_path):
+    """gcc (C, not C++) compiles against the header and links the shared library."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        import pytest
+
+        pytest.skip("gcc not available")
+    exe = tmp_path / "link_check"
+    lib_dir = os.path.dirname(_native.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cabi", "link_check.c"),
+           "-L", lib_dir, "-lanml_b200", f"-Wl,-rpath,{lib_dir}", "-o", str(exe)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "version=100" in run.stdout
