@@ -43,6 +43,7 @@ SIGNATURES = {
     "anml_design_shape": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_void_p)]),
     "anml_design_set_columns": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int]),
     "anml_design_set_spline": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, _c_double_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _c_int32_p]),
+    "anml_design_validate_columns": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "anml_design_download": (C.c_int, [C.c_void_p, _c_double_p, C.c_int64]),
     "anml_design_params": (C.c_int, [C.c_void_p, _c_double_p, C.c_void_p, C.c_int, C.c_int, _c_double_p]),
     "anml_spline_design": (C.c_int, [C.c_int, _c_double_p, C.c_int64, _c_double_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _c_double_p, _c_int32_p]),
@@ -210,6 +211,12 @@ class Design:
         check(load().anml_design_set_spline(self.handle, col0, xp, on_dev, dptr(knots), knots.size, int(degree),
                                             int(ldegree or 0), int(rdegree or 0), int(order), idx_p))
         return idx
+
+    def validate_columns(self, col0: int, ncols: int) -> np.ndarray:
+        """Per-column flags from the device validators: bit 0 = has NaN, bit 1 = has a value <= 0."""
+        flags = (C.c_int * ncols)()
+        check(load().anml_design_validate_columns(self.handle, col0, ncols, flags))
+        return np.frombuffer(flags, dtype=np.int32).copy()
 
     def download(self) -> np.ndarray:
         out = np.empty((self.n_rows, self.n_cols), dtype=np.float64)

@@ -352,6 +352,28 @@ extern "C" int anml_design_set_columns(anml_design* d, int col0, int ncols, cons
     return ANML_OK;
 }
 
+extern "C" int anml_design_validate_columns(const anml_design* d, int col0, int ncols, int* flags_out) {
+    if (!d || !flags_out) return fail(ANML_EINVAL, "anml_design_validate_columns: NULL argument");
+    if (col0 < 0 || ncols <= 0 || col0 + ncols > d->p) return fail(ANML_EINVAL, "anml_design_validate_columns: columns out of range");
+    for (int c = 0; c < ncols; ++c) flags_out[c] = 0;
+    if (d->n == 0) return ANML_OK;
+    CU_TRY(cudaSetDevice(d->device));
+    int* flags = nullptr;
+    CU_TRY(cudaMalloc(&flags, (size_t)ncols * sizeof(int)));
+    cudaError_t e = cudaMemset(flags, 0, (size_t)ncols * sizeof(int));
+    if (e == cudaSuccess) {
+        validate_columns_kernel<<<grid_for(d->n * ncols, 256, d->sm_count), 256>>>(d->X, d->n, d->ld, col0, ncols, flags);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(flags_out, flags, (size_t)ncols * sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(flags);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(ANML_ECUDA, "anml_design_validate_columns: %s", cudaGetErrorString(e));
+    }
+    return ANML_OK;
+}
+
 static int run_spline(int device, int sm_count, const double* x_dev, long long n, const double* knots, int nk, int degree,
                       int ldegree, int rdegree, int order, double* out_dev, long long ld, int col0, int32_t* idx_dev) {
     if (nk < 2 || nk > SPLINE_MAX_KNOTS) return fail(ANML_EINVAL, "spline needs between 2 and %d knots, got %d", SPLINE_MAX_KNOTS, nk);

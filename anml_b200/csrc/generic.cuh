@@ -250,6 +250,22 @@ __global__ void __launch_bounds__(256) add_priors_kernel(const PriorArgs a) {
     }
 }
 
+// Column validators on the device (reference: src/anml/data/validator.py:21-34):
+// flags[c] |= 1 if column c holds a NaN, |= 2 if it holds a value <= 0.
+__global__ void __launch_bounds__(256) validate_columns_kernel(const double* __restrict__ X, long long n, long long ld, int col0,
+                                                               int ncols, int* __restrict__ flags) {
+    const long long total = n * ncols;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / ncols;
+        const int c = (int)(e - i * ncols);
+        const double v = X[i * ld + col0 + c];
+        int f = 0;
+        if (v != v) f |= 1;
+        if (v <= 0.0) f |= 2;
+        if (f) atomicOr(flags + c, f);
+    }
+}
+
 __global__ void fill_kernel(double* p, long long n, double v) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }

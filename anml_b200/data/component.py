@@ -62,13 +62,18 @@ class Component:
         """Cached column (``None`` before ``attach`` / after ``clear``); read-only."""
         return self._value
 
-    def attach(self, df: DataFrame) -> None:
+    def attach(self, df: DataFrame, skip=()) -> None:
+        """Fetch, validate and cache the column.  ``skip`` names validator classes the
+        caller will run itself (``Parameter.attach`` runs ``NoNans`` / ``Positive`` on the
+        device after the upload instead of scanning the column on the host)."""
         if self.key not in df:
             if self.default_value is None:
                 raise KeyError(f"Dataframe doesn't contain column {self.key}.")
             df[self.key] = self.default_value
         column = df[self.key].to_numpy()
         for check in self.validators:
+            if type(check) in skip:
+                continue
             check(self.key, column)
         self._value = column
 

@@ -138,14 +138,29 @@ class Parameter:
         if self.offset is not None:
             self.offset.attach(df)
             self._offset_dev = _native.DeviceBuffer(self.device, np.asarray(self.offset.value, dtype=np.float64))
-        # sizes can depend on the first attach of a spline variable, so resolve them first
+        # sizes can depend on the first attach of a spline variable, so resolve those first;
+        # plain variables attach inside _write_design (validators run on the device)
         for v in self.variables:
-            v.attach(df)
+            if type(v) is not Variable:
+                v.attach(df)
         design = _native.Design(n, self.size, self.device)
         col = 0
+        checks = []
         for v in self.variables:
             v._write_design(design, col, df)
+            want_nan, want_pos = v._device_checks() if hasattr(v, "_device_checks") else (False, False)
+            if want_nan or want_pos:
+                checks.append((col, v.size, v.component.key, want_nan, want_pos))
             col += v.size
+        if checks:
+            # NoNans / Positive (data/validator.py:21-34) in one pass over the uploaded matrix
+            flags = design.validate_columns(0, self.size)
+            for col0, size, key, want_nan, want_pos in checks:
+                f = int(np.bitwise_or.reduce(flags[col0: col0 + size]))
+                if want_nan and (f & 1):
+                    raise ValueError(f"Column '{key}' contains nans.")
+                if want_pos and (f & 2):
+                    raise ValueError(f"Column '{key}' contains nonpositive numbers.")
         self._design, self._design_host = design, None
         for category in _CATEGORIES:
             for prior_type in _TYPES:

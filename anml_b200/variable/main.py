@@ -59,10 +59,22 @@ class Variable:
         self.attach(df)
         return self.component.value[:, np.newaxis]
 
-    # hook used by Parameter.attach: write this variable's columns straight into the
-    # device-resident design matrix (no host hstack)
+    # hooks used by Parameter.attach: write this variable's columns straight into the
+    # device-resident design matrix (no host hstack).  NoNans / Positive are not run on
+    # the host here: Parameter.attach checks all uploaded columns in one device pass and
+    # raises the same ValueError as the host validators.
     def _write_design(self, design, col0: int, df: DataFrame) -> None:
-        design.set_columns(col0, self.get_design_mat(df))
+        from ..data.validator import NoNans, Positive
+
+        self.component.attach(df, skip=(NoNans, Positive))
+        design.set_columns(col0, self.component.value[:, np.newaxis])
+
+    def _device_checks(self):
+        """(wants NoNans, wants Positive) for the columns this variable uploaded."""
+        from ..data.validator import NoNans, Positive
+
+        kinds = {type(v) for v in self.component.validators}
+        return NoNans in kinds, Positive in kinds
 
     def get_direct_prior_params(self, prior_type: str) -> NDArray:
         """(2, size) parameters of the single mat-less prior of this type, or the

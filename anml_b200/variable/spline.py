@@ -64,6 +64,9 @@ class SplineVariable(Variable):
         self.attach(df)
         return self.spline.get_design_mat(self.component.value)
 
+    def _device_checks(self):
+        return False, False  # the component's validators already ran on the host column in attach()
+
     def _write_design(self, design, col0: int, df: DataFrame) -> None:
         self.attach(df)
         sp = self.spline

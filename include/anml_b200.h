@@ -91,6 +91,10 @@ int anml_design_set_columns(anml_design* d, int col0, int ncols, const double* s
  * receives the knot-interval index of every row. */
 int anml_design_set_spline(anml_design* d, int col0, const double* x, int x_on_device, const double* knots,
                            int n_knots, int degree, int ldegree, int rdegree, int order, int32_t* interval_out);
+/* NoNans / Positive validators (src/anml/data/validator.py:21-34) on the uploaded
+ * columns: flags_out[c] (host, ncols ints) gets bit 0 if column col0+c holds a NaN,
+ * bit 1 if it holds a value <= 0. */
+int anml_design_validate_columns(const anml_design* d, int col0, int ncols, int* flags_out);
 int anml_design_download(const anml_design* d, double* host_out, int64_t out_ld);
 /* Parameter.get_params(x, order) (src/anml/parameter/main.py:265-280):
  * order 0 -> out (n), order 1 -> out (n,p), order 2 -> out (n,p,p), host.

@@ -243,3 +243,20 @@ def test_sharded_model_single_rank_uses_the_async_device_path(golden):
     assert direct[0] == o and np.array_equal(direct[1], g) and np.array_equal(direct[2], H)
     res = sharded.fit(np.zeros(x.size), options={"gtol": 1e-8, "maxiter": 50})
     assert np.abs(sharded.gradient(res.x)).max() < 1e-6
+
+
+def test_attach_validators_run_on_the_device():
+    """NoNans (default for string components) and Positive are checked on the uploaded
+    columns; same ValueError text as the host validators of the reference."""
+    from anml_b200.data import Component, NoNans, Positive
+    from anml_b200.parameter import Parameter
+    from anml_b200.variable import Variable
+
+    df = pd.DataFrame({"a": [1.0, 2.0, np.nan, 4.0], "b": [1.0, -2.0, 3.0, 4.0], "c": [1.0, 2.0, 3.0, 4.0]})
+    with pytest.raises(ValueError, match="Column 'a' contains nans."):
+        Parameter([Variable("c"), Variable("a")]).attach(df)
+    with pytest.raises(ValueError, match="Column 'b' contains nonpositive numbers."):
+        Parameter([Variable(Component("b", [NoNans(), Positive()]))]).attach(df)
+    p = Parameter([Variable("b"), Variable("c"), Variable(Component("a"))])  # no validator on 'a': NaN passes through
+    p.attach(df)
+    assert np.isnan(p.design_mat[2, 2]) and p.design_mat[1, 0] == -2.0
