@@ -181,3 +181,35 @@ def test_two_parameter_mean_variance_model(p0, p1, share):
     x = np.concatenate([0.7 * b0, 0.7 * b1])
     want = O.model_eval_fused("gaussian_meanvar", obs, [X0, X1], ["identity", "exp"], x)
     check(gpu_eval_meanvar(X0, X1, obs, x, share=share), want)
+
+
+@pytest.mark.parametrize("share,p", [(True, 9), (False, 9), (True, 70)])
+def test_two_parameter_model_with_offsets_and_links(share, p):
+    """Offsets on both parameters, non-default links; shared design (dual-predictor pass),
+    separate designs (linpred + rowterms) and a wide shared design (blocked Hessian)."""
+    from anml_b200 import _native as N
+
+    rng = np.random.default_rng(p + (1 if share else 0))
+    n = 3001
+    X0 = rng.normal(size=(n, p)); X0[:, 0] = 1.0
+    X1 = X0 if share else np.column_stack([np.ones(n), rng.normal(size=(n, p - 1))])
+    b0 = rng.normal(size=p) * 0.15 / np.sqrt(p / 9)
+    b1 = rng.normal(size=p) * 0.1 / np.sqrt(p / 9)
+    off0, off1 = rng.normal(size=n) * 0.2, rng.normal(size=n) * 0.1
+    mu = np.exp(X0 @ b0 + off0)
+    obs = mu + np.exp(0.5 * (X1 @ b1 + off1)) * rng.normal(size=n)
+    x = np.concatenate([0.8 * b0, 0.8 * b1])
+    want = O.model_eval_fused("gaussian_meanvar", obs, [X0, X1], ["exp", "exp"], x, offsets=[off0, off1])
+    d0 = N.Design(n, p); d0.set_columns(0, X0)
+    d1 = d0 if share else N.Design(n, p)
+    if not share:
+        d1.set_columns(0, X1)
+    o0, o1 = N.DeviceBuffer(0, off0), N.DeviceBuffer(0, off1)
+    m = N.NativeModel(n, "gaussian_meanvar", 2)
+    m.set_param(0, d0, N.LINK_CODES["Exp"], o0)
+    m.set_param(1, d1, N.LINK_CODES["Exp"], o1)
+    m.set_obs(obs)
+    check(m.eval(x), want)
+    if share and p <= 64:
+        m.set_option("force_generic", 1)  # same numbers through linpred + rowterms
+        check(m.eval(x), want)
