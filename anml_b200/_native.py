@@ -52,6 +52,7 @@ SIGNATURES = {
     "anml_model_set_param": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "anml_model_set_obs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "anml_model_set_obs_se": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "anml_model_set_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "anml_model_set_gaussian_prior": (C.c_int, [C.c_void_p, C.c_int, _c_double_p, _c_double_p, C.c_int, _c_double_p, _c_double_p, _c_double_p]),
     "anml_model_set_prior_enabled": (C.c_int, [C.c_void_p, C.c_int]),
     "anml_model_num_coefs": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
@@ -302,6 +303,20 @@ class NativeModel:
             if se.size != self.n_rows:
                 raise ValueError("obs_se length does not match the model")
             check(load().anml_model_set_obs_se(self.handle, se.ctypes.data_as(C.c_void_p), 0))
+
+    def set_weights(self, weights=None, dev_ptr=None, keepalive=None):
+        if dev_ptr is not None:
+            check(load().anml_model_set_weights(self.handle, C.c_void_p(int(dev_ptr)), 1))
+            self._refs.append(keepalive)
+        elif weights is None:
+            check(load().anml_model_set_weights(self.handle, None, 0))
+        else:
+            weights = as_f64(weights, "weights")
+            if weights.size != self.n_rows:
+                raise ValueError("weights length does not match the model")
+            if np.any(weights < 0):
+                raise ValueError("weights must be non-negative")
+            check(load().anml_model_set_weights(self.handle, weights.ctypes.data_as(C.c_void_p), 0))
 
     def set_gaussian_prior(self, k, mean, sd, lin_mat=None, lin_mean=None, lin_sd=None):
         mean, sd = as_f64(mean), as_f64(sd)

@@ -99,8 +99,10 @@ struct anml_model {
     ParamSlot par[2];
     const double* obs = nullptr;
     const double* se = nullptr;
+    const double* weights = nullptr;
     double* obs_owned = nullptr;
     double* se_owned = nullptr;
+    double* weights_owned = nullptr;
     bool prior_enabled = true;
     bool force_generic = false, no_fast = false, no_specialise = false;
     bool force_signed = false;
@@ -630,6 +632,7 @@ extern "C" int anml_model_destroy(anml_model* m) {
     for (int k = 0; k < 2; ++k) free_prior(m->par[k].prior);
     if (m->obs_owned) cudaFree(m->obs_owned);
     if (m->se_owned) cudaFree(m->se_owned);
+    if (m->weights_owned) cudaFree(m->weights_owned);
     for (EventPair& ep : m->ev_pool) {
         cudaEventDestroy(ep.a);
         cudaEventDestroy(ep.b);
@@ -686,6 +689,11 @@ extern "C" int anml_model_set_obs(anml_model* m, const double* obs, int on_devic
 extern "C" int anml_model_set_obs_se(anml_model* m, const double* se, int on_device) {
     if (!m) return fail(ANML_EINVAL, "anml_model_set_obs_se: NULL model");
     return set_row_vector(m, se, on_device, &m->se, &m->se_owned);
+}
+
+extern "C" int anml_model_set_weights(anml_model* m, const double* weights, int on_device) {
+    if (!m) return fail(ANML_EINVAL, "anml_model_set_weights: NULL model");
+    return set_row_vector(m, weights, on_device, &m->weights, &m->weights_owned);
 }
 
 static int upload_vec(double** dst, const std::vector<double>& v) {
@@ -875,7 +883,7 @@ static int run_dual_terms(anml_model* m, cudaStream_t st) {
     memset(&a, 0, sizeof(a));
     a.n = m->n; a.p = d->p; a.link = m->par[0].link; a.link1 = m->par[1].link; a.family = m->family;
     a.beta = m->d_beta + m->par[0].pad_off; a.beta1 = m->d_beta + m->par[1].pad_off;
-    a.obs = m->obs; a.offset = m->par[0].offset; a.offset1 = m->par[1].offset;
+    a.obs = m->obs; a.offset = m->par[0].offset; a.offset1 = m->par[1].offset; a.weights = m->weights;
     a.out_r0 = m->vec[2]; a.out_r1 = m->vec[3]; a.out_w00 = m->vec[4]; a.out_w01 = m->vec[5]; a.out_w11 = m->vec[6];
     a.partials = m->d_partials; a.status = m->d_status;
     int rc = ANML_OK;
@@ -1053,7 +1061,7 @@ static int eval_on_stream(anml_model* m, const double* x_host, int want, cudaStr
     if (m->K == 1 && d0->p <= 64 && !m->force_generic) {
         FusedArgs a;
         a.n = m->n; a.p = d0->p; a.link = m->par[0].link; a.family = m->family; a.fast = m->no_fast ? 0 : 1;
-        a.beta = m->d_beta + m->par[0].pad_off; a.obs = m->obs; a.se = m->se; a.offset = m->par[0].offset;
+        a.beta = m->d_beta + m->par[0].pad_off; a.obs = m->obs; a.se = m->se; a.offset = m->par[0].offset; a.weights = m->weights;
         a.rvec = nullptr; a.wvec = nullptr; a.partials = nullptr; a.status = nullptr;
         TRY(run_fused_block(m, d0, a, hess, 0, 0, 0, true, false, true, st));
     } else {
@@ -1091,7 +1099,7 @@ static int eval_general(anml_model* m, int want, cudaStream_t st) {
         RowTermsArgs ra;
         ra.n = m->n; ra.family = m->family; ra.nparams = K; ra.link0 = m->par[0].link; ra.link1 = (K == 2) ? m->par[1].link : 0;
         ra.fast = m->no_fast ? 0 : 1;
-        ra.y0 = m->vec[0]; ra.y1 = m->vec[1]; ra.obs = m->obs; ra.se = m->se;
+        ra.y0 = m->vec[0]; ra.y1 = m->vec[1]; ra.obs = m->obs; ra.se = m->se; ra.weights = m->weights;
         ra.r0 = m->vec[2]; ra.r1 = m->vec[3]; ra.w00 = m->vec[4]; ra.w01 = m->vec[5]; ra.w11 = m->vec[6];
         ra.obj_partials = m->d_partials; ra.status = m->d_status;
         const int rgrid = grid_for(m->n, 256, m->sm_count, 8);

@@ -43,6 +43,7 @@ struct FusedArgs {
     const double* obs;     // device (n)            [MODE 0]
     const double* se;      // device (n) or null    [MODE 0]
     const double* offset;  // device (n) or null    [MODE 0]
+    const double* weights; // device (n) or null: per-row likelihood weights (trimming)
     const double* rvec;    // device (n)            [MODE 1]
     const double* wvec;    // device (n)            [MODE 1]
     double* partials;      // [gridDim.x][EL]
@@ -209,9 +210,10 @@ __global__ void __launch_bounds__(256, 1) fused_eval_kernel(const __grid_constan
                 const double ob = a.obs[row];
                 const double se = a.se ? a.se[row] : 1.0;
                 const RowTerms1 rt = row_terms1(a.family, a.link, a.fast != 0, y, ob, se);
-                objacc += rt.l;
-                rr = rt.r;
-                ww = rt.w;
+                const double wt = a.weights ? a.weights[row] : 1.0;
+                objacc += wt * rt.l;
+                rr = wt * rt.r;
+                ww = wt * rt.w;
                 bad_domain |= !rt.ok;
             }
         } else if (MODE == 2) {
@@ -243,12 +245,13 @@ __global__ void __launch_bounds__(256, 1) fused_eval_kernel(const __grid_constan
                 if (a.offset) y0 += a.offset[row];
                 if (a.offset1) y1 += a.offset1[row];
                 const RowTerms2 rt = row_terms2(a.link, a.link1, y0, y1, a.obs[row]);
-                objacc += rt.l;
-                a.out_r0[row] = rt.r0;
-                a.out_r1[row] = rt.r1;
-                a.out_w00[row] = rt.w00;
-                a.out_w01[row] = rt.w01;
-                a.out_w11[row] = rt.w11;
+                const double wt = a.weights ? a.weights[row] : 1.0;
+                objacc += wt * rt.l;
+                a.out_r0[row] = wt * rt.r0;
+                a.out_r1[row] = wt * rt.r1;
+                a.out_w00[row] = wt * rt.w00;
+                a.out_w01[row] = wt * rt.w01;
+                a.out_w11[row] = wt * rt.w11;
                 bad_domain |= !rt.ok;
             }
             // no gradient / Hessian here: both slots are consumed, re-arm them

@@ -293,11 +293,19 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
                 const double y = transpose_reduce8(part, g);
                 if (valid) {
                     const RowTerms1 rt = row_terms1<true>(a.family, a.link, (a.fast & 1) != 0, y + off, ob, se);
-                    objacc += rt.l;
-                    rr = rt.r;
-                    ww = rt.w;
-                    sc = rt.sw;
                     bad_domain |= !rt.ok;
+                    if (a.weights) {  // per-row likelihood weight (>= 0): scales l, r, w
+                        const double wt = a.weights[row];
+                        objacc += wt * rt.l;
+                        rr = wt * rt.r;
+                        ww = wt * rt.w;
+                        sc = sqrt(wt) * rt.sw;
+                    } else {
+                        objacc += rt.l;
+                        rr = rt.r;
+                        ww = rt.w;
+                        sc = rt.sw;
+                    }
                 }
             } else if (valid) {
                 rr = a.rvec[row];

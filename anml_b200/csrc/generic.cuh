@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) tensor2_kernel(const double* __restrict__
 struct RowTermsArgs {
     long long n;
     int family, nparams, link0, link1, fast;
-    const double *y0, *y1, *obs, *se;
+    const double *y0, *y1, *obs, *se, *weights;
     double *r0, *r1, *w00, *w01, *w11;
     double* obj_partials;  // [gridDim.x]
     int* status;
@@ -96,15 +96,17 @@ __global__ void __launch_bounds__(256) rowterms_kernel(const RowTermsArgs a) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
         if (a.nparams == 1) {
             const RowTerms1 t = row_terms1(a.family, a.link0, a.fast != 0, a.y0[i], a.obs[i], a.se ? a.se[i] : 1.0);
-            l += t.l;
-            a.r0[i] = t.r;
-            a.w00[i] = t.w;
+            const double wt = a.weights ? a.weights[i] : 1.0;
+            l += wt * t.l;
+            a.r0[i] = wt * t.r;
+            a.w00[i] = wt * t.w;
             bad |= !t.ok;
         } else {
             const RowTerms2 t = row_terms2(a.link0, a.link1, a.y0[i], a.y1[i], a.obs[i]);
-            l += t.l;
-            a.r0[i] = t.r0; a.r1[i] = t.r1;
-            a.w00[i] = t.w00; a.w01[i] = t.w01; a.w11[i] = t.w11;
+            const double wt = a.weights ? a.weights[i] : 1.0;
+            l += wt * t.l;
+            a.r0[i] = wt * t.r0; a.r1[i] = wt * t.r1;
+            a.w00[i] = wt * t.w00; a.w01[i] = wt * t.w01; a.w11[i] = wt * t.w11;
             bad |= !t.ok;
         }
     }

@@ -110,7 +110,10 @@ class Model:
             se = np.asarray(self.data.obs_se.value, dtype=np.float64)
             if np.all(se == 1.0):
                 se = None  # the default column (data/example.py:21): skip reading it
-        self._configure(len(df), obs=obs, se=se)
+        weights = None
+        if hasattr(self.data, "weights"):  # optional component: per-row likelihood weights (trimming)
+            weights = np.asarray(self.data.weights.value, dtype=np.float64)
+        self._configure(len(df), obs=obs, se=se, weights=weights)
 
     def attach_device(self, n_rows: int, obs_dev_ptr: int, se_dev_ptr: Optional[int] = None, keepalive=None) -> None:
         """Configure from parameters that were given device-resident designs
@@ -118,7 +121,7 @@ class Model:
         _native.require_device(self.device)
         self._configure(n_rows, obs_ptr=obs_dev_ptr, se_ptr=se_dev_ptr, keepalive=keepalive)
 
-    def _configure(self, n, obs=None, se=None, obs_ptr=None, se_ptr=None, keepalive=None):
+    def _configure(self, n, obs=None, se=None, obs_ptr=None, se_ptr=None, keepalive=None, weights=None):
         nm = _native.NativeModel(n, self.family, len(self.parameters), self.device)
         for k, p in enumerate(self.parameters):
             if p.device_design is None:
@@ -135,6 +138,8 @@ class Model:
             nm.set_obs(obs)
             if se is not None:
                 nm.set_obs_se(se)
+        if weights is not None:
+            nm.set_weights(weights)
         for k, p in enumerate(self.parameters):
             direct = p.prior_dict["direct"]["GaussianPrior"]
             linear = p.prior_dict["linear"]["GaussianPrior"]

@@ -114,6 +114,9 @@ int anml_model_destroy(anml_model* m);
 int anml_model_set_param(anml_model* m, int k, const anml_design* design, int link, const double* offset_dev);
 int anml_model_set_obs(anml_model* m, const double* obs, int on_device);
 int anml_model_set_obs_se(anml_model* m, const double* obs_se /* NULL = 1.0 */, int on_device);
+/* optional per-row likelihood weights (>= 0; NULL = all ones): every row's NLL term, and
+ * with it its gradient and Hessian contribution, is multiplied by its weight (trimming) */
+int anml_model_set_weights(anml_model* m, const double* weights, int on_device);
 /* combined Gaussian priors of Parameter k, as Parameter.prior_dict holds them
  * (src/anml/parameter/main.py:167-227): direct (mean, sd) of length p_k (sd may
  * be +inf) and linear (mat (m, p_k), mean (m), sd (m)), m may be 0. */

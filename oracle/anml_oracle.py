@@ -226,7 +226,7 @@ def model_eval_literal(family, obs, Xs, links, x, offsets=None, obs_se=None, pri
     return _add_priors(obj, grad, hess, betas, starts, priors)
 
 
-def model_eval_fused(family, obs, Xs, links, x, offsets=None, obs_se=None, priors=None, chunk=1 << 20):
+def model_eval_fused(family, obs, Xs, links, x, offsets=None, obs_se=None, priors=None, chunk=1 << 20, weights=None):
     """Same quantities without the (n,p,p) tensor (last lines):
         r_k  = dl_k f_k'                 g_k  = X_k^T r_k
         w_kl = d2l_kl f_k' f_l' + [k==l] dl_k f_k''     H_kl = X_k^T diag(w_kl) X_l
@@ -250,6 +250,11 @@ def model_eval_fused(family, obs, Xs, links, x, offsets=None, obs_se=None, prior
         f1 = [link_eval(links[k], ys[k], 1) for k in range(K)]
         f2 = [link_eval(links[k], ys[k], 2) for k in range(K)]
         l, dl, d2l = family_terms(family, obs[lo:hi], th, None if obs_se is None else obs_se[lo:hi])
+        if weights is not None:  # per-row likelihood weights scale every term of the row
+            wt = np.asarray(weights, float)[lo:hi]
+            l = wt * l
+            dl = [wt * d for d in dl]
+            d2l = {k: wt * v for k, v in d2l.items()}
         obj += float(np.sum(l))
         for k in range(K):
             sk = slice(starts[k], starts[k + 1])

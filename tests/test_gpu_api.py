@@ -260,3 +260,26 @@ def test_attach_validators_run_on_the_device():
     p = Parameter([Variable("b"), Variable("c"), Variable(Component("a"))])  # no validator on 'a': NaN passes through
     p.attach(df)
     assert np.isnan(p.design_mat[2, 2]) and p.design_mat[1, 0] == -2.0
+
+
+def test_model_picks_up_a_weights_component():
+    from anml_b200.data import Component, DataPrototype, NoNans
+    from anml_b200.model import Model
+
+    rng = np.random.default_rng(8)
+    n, p = 2000, 4
+    X = rng.normal(size=(n, p)); X[:, 0] = 1.0
+    obs = X @ (rng.normal(size=p) * 0.3) + rng.normal(size=n)
+    wts = rng.uniform(0, 1, size=n)
+    df = frame_from(X, {"obs": obs, "wt": wts})
+    data = DataPrototype({"obs": Component("obs", [NoNans()]), "weights": Component("wt", [NoNans()])})
+    model = Model("gaussian", data, [make_parameter(p)])
+    model.attach(df)
+    x = rng.normal(size=p)
+    want = O.model_eval_fused("gaussian", obs, [X], ["identity"], x, weights=wts)
+    got = model.evaluate(x)
+    assert abs(got[0] - want[0]) <= 1e-10 * abs(want[0])
+    assert np.abs(got[2] - want[2]).max() <= 1e-9 * np.abs(want[2]).max()
+    res = model.fit()
+    wls = np.linalg.solve((X.T * wts) @ X, (X.T * wts) @ obs)  # weighted least squares in closed form
+    assert np.abs(res.x - wls).max() < 1e-8

@@ -213,3 +213,28 @@ def test_two_parameter_model_with_offsets_and_links(share, p):
     if share and p <= 64:
         m.set_option("force_generic", 1)  # same numbers through linpred + rowterms
         check(m.eval(x), want)
+
+
+@pytest.mark.parametrize("family,link,p", [("binomial", "expit", 64), ("gaussian", "exp", 5), ("poisson", "exp", 20)])
+def test_row_weights_scale_every_term(family, link, p):
+    """Per-row likelihood weights (trimming): fused path, symmetric variant and general path."""
+    from anml_b200 import _native as N
+
+    X, obs, se, off, link, x = make_problem(family, 4003, p, seed=p, link=link, with_offset=True)
+    wts = np.random.default_rng(p).uniform(0.0, 2.0, size=obs.size)
+    wts[::7] = 0.0  # trimmed rows
+    want = O.model_eval_fused(family, obs, [X], [link], x, offsets=[off], weights=wts)
+    for opts in ((), (("no_warp_specialisation", 1),), (("force_generic", 1),)):
+        d = N.Design(X.shape[0], p); d.set_columns(0, X)
+        ob = N.DeviceBuffer(0, off)
+        m = N.NativeModel(X.shape[0], family, 1)
+        m.set_param(0, d, N.LINK_CODES[LINK_NAME[link]], ob)
+        m.set_obs(obs)
+        m.set_weights(wts)
+        for k, v in opts:
+            m.set_option(k, v)
+        check(m.eval(x), want)
+    with pytest.raises(ValueError):
+        m.set_weights(-wts - 1.0)
+    m.set_weights(None)  # back to unweighted
+    check(m.eval(x), O.model_eval_fused(family, obs, [X], [link], x, offsets=[off]))
