@@ -93,6 +93,20 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// one lane of the (converged) warp, chosen by the hardware: lets ptxas keep the TMA
+// issue on the uniform datapath instead of a divergent lane-0 branch
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "elect.sync _|P1, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ double shfl_xor_d(double v, int mask) { return __shfl_xor_sync(FULL_MASK, v, mask); }
 __device__ __forceinline__ double shfl_idx_d(double v, int src) { return __shfl_sync(FULL_MASK, v, src); }
 

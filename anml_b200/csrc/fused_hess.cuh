@@ -56,7 +56,8 @@ struct HessCfg {
     static constexpr int TEAM_BYTES = NBUF * BUF_BYTES;
     static constexpr int EL = (2 * NT + NB8 + 1) * 32;
     static constexpr int SMEM_BYTES = 1024 + TEAMS * TEAM_BYTES + TEAMS * NBUF * 32 * 4 /*sign masks*/ + TEAMS * NBUF * 2 * 8 /*full barriers, ready flags*/ +
-                                      16 * NB16 * 8 /*beta*/ + TEAMS * HELPERS * (NB8 + 1) * 32 * 8 /*helper g, obj*/;
+                                      16 * NB16 * 8 /*beta*/ + TEAMS * HELPERS * (NB8 + 1) * 32 * 8 /*helper g, obj; transpose scratch*/ +
+                                      TEAMS * HELPERS * 64 * 8 /*helper r, sqrt|w|*/;
 };
 
 // DMMA without `volatile`: ptxas may hoist the next k-step's LDS above it
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
     const uint32_t bars_base = signs_base + TEAMS * NBUF * 32 * 4;
     const uint32_t beta_base = bars_base + TEAMS * NBUF * 2 * 8;
     const uint32_t hrec_base = beta_base + 16 * NB16 * 8;
+    const uint32_t hterm_base = hrec_base + TEAMS * C::HELPERS * (NB8 + 1) * 256;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -250,6 +252,8 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
         bool bad_domain = false;
         // lane (g,t) ends up owning the row of k-step s == g, sub-row t
         const int R = 16 * (g >> 2) + 8 * ((g >> 1) & 1) + (g & 1) + 2 * t;
+        const uint32_t tr_u32 = hrec_base + (team * C::HELPERS + hid) * (NB8 + 1) * 256;  // transpose scratch (epilogue record later)
+        const uint32_t ht_u32 = hterm_base + (team * C::HELPERS + hid) * 512;             // [0..31] r, [32..63] sqrt|w| of the block
         // this lane's slice of beta (columns 16j + 2g, +1) stays in registers
         double2 bsl[NB16];
 #pragma unroll
@@ -290,7 +294,24 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
                     }
                     part[s] = d;
                 }
-                const double y = transpose_reduce8(part, g);
+                // 8 partial sums per lane -> one row total per lane, through shared memory: lane (g,t)
+                // stores part[s] at [s][g][t] (row pitch 36 doubles: conflict-free), then lane (s'=g, t)
+                // adds the 8 entries [g][*][t].  24 instructions with ILP instead of ~60 dependent
+                // shuffle/select instructions (every helper instruction costs the tensor warp cycles).
+                double y;
+                if (NB8 == 8) {
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) sts64(tr_u32 + (s * 36 + lane) * 8, part[s]);
+                    __syncwarp();
+                    double q0 = lds64(tr_u32 + (g * 36 + 0 * 4 + t) * 8), q1 = lds64(tr_u32 + (g * 36 + 1 * 4 + t) * 8);
+                    double q2 = lds64(tr_u32 + (g * 36 + 2 * 4 + t) * 8), q3 = lds64(tr_u32 + (g * 36 + 3 * 4 + t) * 8);
+                    double q4 = lds64(tr_u32 + (g * 36 + 4 * 4 + t) * 8), q5 = lds64(tr_u32 + (g * 36 + 5 * 4 + t) * 8);
+                    double q6 = lds64(tr_u32 + (g * 36 + 6 * 4 + t) * 8), q7 = lds64(tr_u32 + (g * 36 + 7 * 4 + t) * 8);
+                    y = ((q0 + q1) + (q2 + q3)) + ((q4 + q5) + (q6 + q7));
+                    __syncwarp();
+                } else {
+                    y = transpose_reduce8(part, g);
+                }
                 if (valid) {
                     const RowTerms1 rt = row_terms1<true>(a.family, a.link, (a.fast & 1) != 0, y + off, ob, se);
                     bad_domain |= !rt.ok;
@@ -314,13 +335,18 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
             }
             if (SIGNED) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sign_u32 + buf * 128 + lane * 4), "r"(ww < 0.0 ? 0x80000000u : 0u) : "memory");
             // ---- pass 2: gradient, and rescale the block in place to sqrt(|w|) x
+            // (r, sqrt|w|) of the 32 rows go through shared memory: 2 stores + broadcast loads
+            // instead of 32 shuffles
+            sts64(ht_u32 + lane * 8, rr);
+            sts64(ht_u32 + 256 + lane * 8, sc);
+            __syncwarp();
 #pragma unroll
             for (int s = 0; s < 8; ++s) {
                 const int xr = 2 * t + (s & 1);
                 const int rowi = 16 * (s >> 2) + 8 * ((s >> 1) & 1) + xr;
                 const uint32_t rp = bp + rowi * 128 + ((g ^ xr) << 4);
-                const double rv = shfl_idx_d(rr, 4 * s + t);
-                const double sv = shfl_idx_d(sc, 4 * s + t);
+                const double rv = lds64(ht_u32 + (4 * s + t) * 8);
+                const double sv = lds64(ht_u32 + 256 + (4 * s + t) * 8);
 #pragma unroll
                 for (int j = 0; j < NB16; ++j) {
                     const double2 v = lds128(rp + j * 4096);
