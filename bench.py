@@ -329,8 +329,9 @@ def run_gpu(args):
         hbm_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         flops = float(n) * p * (p + 1)
         bytes_alg = 8.0 * n * p + 8.0 * n
-        achieved_tf = flops / (kernel_ms * 1e-3) / 1e12
-        achieved_gbs = bytes_alg / (grad_kernel_ms * 1e-3) / 1e9
+        achieved_tf = flops / (kernel_ms * 1e-3) / 1e12 if kernel_ms > 0 else 0.0
+        # (the general path, p > 64, has no single timed gradient kernel)
+        achieved_gbs = bytes_alg / (grad_kernel_ms * 1e-3) / 1e9 if grad_kernel_ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": 1e3 / ms_step, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -343,8 +344,8 @@ def run_gpu(args):
                     "h2d_bytes_per_step": int(8 * (p + 64)), "d2h_bytes_per_step": int(8 * (2 + p + p * p)),
                     "note": "Model/ShardedModel.evaluate(x): host x -> host (obj, grad, Hessian); X attached once, as the reference caches design_mat"},
             "gpu_launches": int(all_launches),
-            "roofline": {"kernel": "fused_hess_kernel", "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": NCU_DRAM_BYTES_PER_ROW * n,
+            "roofline": {"kernel": "fused_hess_kernel" if p <= 64 else "wide_hessian_kernel", "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf, "traffic": NCU_DRAM_BYTES_PER_ROW * n if p == 64 else None,
                          "kernel_ms": kernel_ms, "flops_per_launch": flops,
                          "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (FP64 is absent from MEASURED_PEAKS.json)",
                          "traffic_source": "ncu --set full capture at n=1e7 (profiles/), dram bytes per row x rows"},
