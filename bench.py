@@ -256,7 +256,6 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    peak_tf = dgemm_peak_tflops(torch, dev)
     sampler = ClockSampler(local_rank) if rank == 0 else None
 
     # ---- device-timed steps: X resident, coefficient vector from host, result left on the device
@@ -318,6 +317,9 @@ def run_gpu(args):
     grad_kernel_ms = float(tg[0])
 
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    # FP64 roofline denominator: cuBLAS DGEMM on this GPU, measured after the timed regions so that its
+    # power draw does not leak into the clock / power samples above
+    peak_tf = dgemm_peak_tflops(torch, dev)
 
     if rank == 0:
         peaks = {}
@@ -355,6 +357,25 @@ def run_gpu(args):
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
+            # one-off ingest (Parameter.attach from a pandas frame: upload + device scatter + device
+            # validators) on a bounded sample, for transparency about what `e2e` leaves outside
+            try:
+                import pandas as pd
+
+                n_in = min(n_total, 1_000_000)
+                rng = np.random.default_rng(SEED + 9)
+                df = pd.DataFrame({f"cov{j}": rng.standard_normal(n_in) for j in range(p - 1)})
+                par_in = Parameter([Variable(Component("intercept", default_value=1.0))] + [Variable(f"cov{j}") for j in range(p - 1)],
+                                   transform=Expit(), device=local_rank)
+                par_in.attach(df)  # warm-up
+                t_in = time.perf_counter()
+                par_in.attach(df)
+                t_in = time.perf_counter() - t_in
+                line["ingest"] = {"rows_per_s": n_in / t_in, "GBps": n_in * p * 8 / t_in / 1e9,
+                                  "sample": f"Parameter.attach of a {n_in} x {p} pandas frame (host float64 columns)"}
+                del par_in, df
+            except Exception as exc:  # never let the optional extra break the bench line
+                line["ingest"] = {"error": repr(exc)}
             n_sample = min(n_total, args.cpu_rows)
             Xc, oc, bt = cpu_sample(n_sample, p, SEED + 2)
             times = cpu_eval_seconds(Xc, oc, 0.5 * bt, p, reps=3, warmup=1)
