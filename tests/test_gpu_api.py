@@ -283,3 +283,47 @@ def test_model_picks_up_a_weights_component():
     res = model.fit()
     wls = np.linalg.solve((X.T * wts) @ X, (X.T * wts) @ obs)  # weighted least squares in closed form
     assert np.abs(res.x - wls).max() < 1e-8
+
+
+def test_empty_frame_gives_prior_only_terms():
+    """Zero rows: likelihood sums are empty, only the Gaussian prior remains (NumPy semantics of
+    the reference: sums over empty arrays are 0)."""
+    from anml_b200.data import DataExample
+    from anml_b200.model import Model
+    from anml_b200.prior import GaussianPrior
+
+    p = 5
+    df = pd.DataFrame({**{f"cov{j}": np.empty(0) for j in range(p - 1)}, "obs": np.empty(0)})
+    par = make_parameter(p, "expit", var_priors=[GaussianPrior(mean=0.5, sd=2.0)])
+    model = Model("binomial", DataExample("obs", "obs_se"), [par])
+    model.attach(df)
+    assert par.design_mat.shape == (0, p)
+    assert par.get_params(np.ones(p)).shape == (0,)
+    assert par.get_params(np.ones(p), order=2).shape == (0, p, p)
+    x = np.linspace(-1, 1, p)
+    o, g, H = model.evaluate(x)
+    assert abs(o - par.prior_objective(x)) < 1e-14
+    np.testing.assert_allclose(g, par.prior_gradient(x), atol=1e-15)
+    np.testing.assert_allclose(H, par.prior_hessian(x), atol=1e-15)
+
+
+def test_prediction_on_a_new_frame_reuses_spline_knots():
+    """get_params(x, df_new): knots come from the first attached frame only
+    (variable/spline.py:103-107); the new frame is evaluated with them."""
+    from anml_b200.getter import SplineGetter
+    from anml_b200.parameter import Exp, Parameter
+    from anml_b200.variable import SplineVariable, Variable
+
+    r = np.random.default_rng(3)
+    df1 = pd.DataFrame({"x": r.uniform(0, 1, 500), "z": r.normal(size=500)})
+    sv = SplineVariable("x", SplineGetter(np.linspace(0, 1, 6), degree=3, knots_type="rel_domain"))
+    par = Parameter([sv, Variable("z")], transform=Exp())
+    beta = r.normal(size=9) * 0.2
+    par.get_params(beta, df1)
+    knots = sv.spline.knots.copy()
+    df2 = pd.DataFrame({"x": r.uniform(0.1, 0.9, 50), "z": r.normal(size=50)})
+    pred = par.get_params(beta, df2, order=0)
+    np.testing.assert_array_equal(sv.spline.knots, knots)
+    X2 = np.column_stack([O.spline_design(knots, 3, df2["x"].to_numpy()), df2["z"].to_numpy()])
+    np.testing.assert_allclose(pred, np.exp(X2 @ beta), rtol=1e-13)
+    np.testing.assert_array_equal(par.design_mat, X2)
