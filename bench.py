@@ -86,6 +86,19 @@ def cpu_eval_seconds(X, obs, x, p, reps, warmup=1):
     return times[warmup:]
 
 
+def cpu_literal_rows_per_s(X, obs, x, p):
+    from oracle import anml_oracle as O
+
+    priors = [{"direct": (np.zeros(p), np.ones(p))}]
+    best = float("inf")
+    for _ in range(3):
+        t0 = time.perf_counter()
+        O.model_eval_literal("binomial", obs, [X], ["expit"], x, priors=priors)
+        best = min(best, time.perf_counter() - t0)
+    return {"rows_per_s": X.shape[0] / best, "rows": int(X.shape[0]),
+            "note": "J (n,p) and T (n,p,p) materialised as the reference's get_params orders 1 and 2 do; best of 3"}
+
+
 def run_reference(args):
     """`--impl reference`: the reference's CPU route for this path, all host threads.
     anml is pure NumPy and has no model layer; the timed code is the oracle port of
@@ -386,6 +399,10 @@ def run_gpu(args):
                 "sample": f"{n_sample} of {n_total} rows, best of 3, evals/s extrapolated linearly in rows; NumPy oracle route "
                           f"(chunked X^T diag(w) X), {api} {cores} threads of {os.cpu_count()} cores",
                 "rows_per_s": n_sample / sec}
+            # the reference's literal route (get_params order 2 materialises an (n,p,p) tensor,
+            # parameter/main.py:278-280) at the largest n whose tensor stays under ~1 GB
+            n_lit = max(16, min(n_sample, int(1e9 / (8.0 * p * p))))
+            line["cpu_baseline"]["literal_route"] = cpu_literal_rows_per_s(Xc[:n_lit], oc[:n_lit], 0.5 * bt, p)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
