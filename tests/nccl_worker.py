@@ -1,0 +1,85 @@
+"""Worker for tests/test_gpu_multi.py: one rank of a row-sharded evaluation + fit over NCCL.
+
+Launched by ``python -m torch.distributed.run``; every rank rebuilds the same seeded
+host data set, keeps its own row block on its GPU and joins the ShardedModel.  Rank 0
+checks the all-reduced result against the NumPy oracle on the full data set and the
+fitted coefficients against a trust-constr run on the oracle callbacks.
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    import pandas as pd
+    import torch
+    import torch.distributed as dist
+
+    from anml_b200.data import Component, DataExample
+    from anml_b200.distributed import NativeLocalEvaluator, ShardedModel, shard_rows
+    from anml_b200.model import Model
+    from anml_b200.parameter import Expit, Parameter
+    from anml_b200.prior import GaussianPrior
+    from anml_b200.variable import Variable
+    from oracle import anml_oracle as O
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local_rank)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        rng = np.random.default_rng(20261019)
+        n, p = 200_003, 24
+        X = rng.normal(size=(n, p))
+        X[:, 0] = 1.0
+        beta = rng.normal(size=p) * 0.2
+        obs = (rng.uniform(size=n) < 1 / (1 + np.exp(-X @ beta))).astype(float)
+        lo, hi = shard_rows(n, world, rank)
+        df = pd.DataFrame({f"c{j}": X[lo:hi, j] for j in range(1, p)})
+        df["obs"] = obs[lo:hi]
+
+        prior = [GaussianPrior(mean=0.0, sd=2.0)]
+        variables = [Variable(Component("intercept", default_value=1.0), priors=prior)]
+        variables += [Variable(f"c{j}", priors=prior) for j in range(1, p)]
+        par = Parameter(variables, transform=Expit(), device=local_rank)
+        model = Model("binomial", DataExample("obs", "obs_se"), [par], device=local_rank)
+        model.attach(df)
+        model.set_prior_enabled(rank == 0)  # the prior is counted once
+        sharded = ShardedModel(NativeLocalEvaluator(model, torch.device("cuda", local_rank)))
+
+        priors = [{"direct": (np.zeros(p), np.full(p, 2.0))}]
+        x = 0.5 * beta
+        o, g, h = sharded.unpack(sharded.evaluate_collective(x, True))
+        want = O.model_eval_fused("binomial", obs, [X], ["expit"], x, priors=priors)
+        assert abs(o - want[0]) <= 1e-10 * abs(want[0]), (o, want[0])
+        assert np.abs(g - want[1]).max() <= 1e-10 * np.abs(want[1]).max()
+        assert np.abs(h - want[2]).max() <= 1e-9 * np.abs(want[2]).max()
+        assert np.array_equal(h, h.T)
+        # every rank holds the same bits after the all-reduce
+        mine = torch.tensor(np.concatenate([[o], g, h.ravel()]), device=f"cuda:{local_rank}")
+        ref0 = mine.clone()
+        dist.broadcast(ref0, src=0)
+        assert torch.equal(mine, ref0)
+
+        res = sharded.fit(np.zeros(p), options={"gtol": 1e-10})
+        if rank == 0:
+            from scipy.optimize import minimize
+
+            f = lambda z: O.model_eval_fused("binomial", obs, [X], ["expit"], z, priors=priors)
+            ref = minimize(lambda z: f(z)[0], np.zeros(p), jac=lambda z: f(z)[1], hess=lambda z: f(z)[2], method="trust-constr",
+                           options={"gtol": 1e-10, "xtol": 1e-14, "maxiter": 200})
+            err = np.abs(res.x - ref.x).max()
+            assert err < 1e-8, err
+            print(f"NCCL_SHARDED_OK world={world} evals={sharded.num_evaluations} coef_err={err:.2e}", flush=True)
+        else:
+            assert res is None
+    finally:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
