@@ -17,6 +17,7 @@
 #include "fused_hess.cuh"
 #include "generic.cuh"
 #include "spline.cuh"
+#include "upload.cuh"
 #include "wide_hessian.cuh"
 
 using namespace anml;
@@ -67,8 +68,6 @@ struct anml_design {
     bool owned = false;
     CUtensorMap tmap;    // box 16 rows x 16 cols, 128B swizzle
     CUtensorMap tmap32;  // box 32 rows x 16 cols, 128B swizzle
-    double* stage = nullptr;  // upload staging buffer, kept between set_columns calls
-    long long stage_elems = 0;
     int sm_count = 0;
 };
 
@@ -170,7 +169,12 @@ extern "C" int anml_dev_free(int device, void* dev) {
     return ANML_OK;
 }
 extern "C" int anml_dev_upload(int device, void* dst, const void* src, int64_t bytes) {
+    if (bytes < 0 || (bytes > 0 && (!dst || !src))) return fail(ANML_EINVAL, "anml_dev_upload: bad arguments");
     CU_TRY(cudaSetDevice(device));
+    if (bytes % 8 == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0 && (reinterpret_cast<uintptr_t>(src) & 7) == 0) {
+        CU_TRY(upload_vector(device, 0, static_cast<double*>(dst), static_cast<const double*>(src), bytes / 8));
+        return ANML_OK;
+    }
     CU_TRY(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyHostToDevice));
     return ANML_OK;
 }
@@ -284,7 +288,6 @@ extern "C" int anml_design_destroy(anml_design* d) {
     if (!d) return ANML_OK;
     cudaSetDevice(d->device);
     if (d->owned && d->X) cudaFree(d->X);
-    if (d->stage) cudaFree(d->stage);
     delete d;
     return ANML_OK;
 }
@@ -317,40 +320,13 @@ extern "C" int anml_design_set_columns(anml_design* d, int col0, int ncols, cons
         CU_TRY(cudaDeviceSynchronize());
         return ANML_OK;
     }
-    // host source: stage through a bounded dense device buffer (kept in the handle), chunk of rows at a time
-    const long long max_elems = 1LL << 25;  // 256 MiB of doubles
-    long long rows_per_chunk = max_elems / ncols;
-    if (rows_per_chunk < 1) rows_per_chunk = 1;
-    if (rows_per_chunk > d->n) rows_per_chunk = d->n;
-    if (d->stage_elems < rows_per_chunk * ncols) {
-        if (d->stage) CU_TRY(cudaFree(d->stage));
-        d->stage = nullptr;
-        d->stage_elems = 0;
-        CU_TRY(cudaMalloc(&d->stage, (size_t)rows_per_chunk * ncols * sizeof(double)));
-        d->stage_elems = rows_per_chunk * ncols;
+    // host source: pinned lanes filled by a few host threads, DMA + column scatter per lane (upload.cuh)
+    const UploadJob job{d->X, d->ld, col0, d->n, ncols, src, src_ld};
+    const cudaError_t e = upload_run(d->device, d->sm_count, job);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(ANML_ECUDA, "anml_design_set_columns: %s", cudaGetErrorString(e));
     }
-    double* tmp = d->stage;
-    for (long long r0 = 0; r0 < d->n; r0 += rows_per_chunk) {
-        const long long rows = (d->n - r0 < rows_per_chunk) ? d->n - r0 : rows_per_chunk;
-        cudaError_t e;
-        if (src_ld == ncols)  // dense block: one linear copy
-            e = cudaMemcpyAsync(tmp, src + r0 * src_ld, (size_t)rows * ncols * sizeof(double), cudaMemcpyHostToDevice, 0);
-        else
-            e = cudaMemcpy2DAsync(tmp, (size_t)ncols * sizeof(double), src + r0 * src_ld, (size_t)src_ld * sizeof(double),
-                                  (size_t)ncols * sizeof(double), (size_t)rows, cudaMemcpyHostToDevice, 0);
-        if (e == cudaSuccess) {
-            scatter_columns_kernel<<<grid_for(rows * ncols, 256, d->sm_count), 256>>>(d->X + r0 * d->ld, rows, d->ld, col0, ncols, tmp, ncols);
-            e = cudaGetLastError();
-        }
-        // the next chunk reuses the staging buffer: wait for the scatter (stream order also covers it,
-        // the explicit sync keeps error reporting local)
-        if (e == cudaSuccess && r0 + rows_per_chunk < d->n) e = cudaStreamSynchronize(0);
-        if (e != cudaSuccess) {
-            (void)cudaGetLastError();
-            return fail(ANML_ECUDA, "anml_design_set_columns: %s", cudaGetErrorString(e));
-        }
-    }
-    CU_TRY(cudaStreamSynchronize(0));
     return ANML_OK;
 }
 
@@ -444,7 +420,7 @@ extern "C" int anml_design_set_spline(anml_design* d, int col0, const double* x,
     const size_t nn = (size_t)(d->n > 0 ? d->n : 1);
     if (!x_on_device) {
         CU_TRY(cudaMalloc(&x_tmp, nn * sizeof(double)));
-        cudaError_t e = cudaMemcpy(x_tmp, x, (size_t)d->n * sizeof(double), cudaMemcpyHostToDevice);
+        cudaError_t e = upload_vector(d->device, d->sm_count, x_tmp, x, d->n);
         if (e != cudaSuccess) {
             cudaFree(x_tmp);
             return fail(ANML_ECUDA, "upload of spline abscissae failed: %s", cudaGetErrorString(e));
@@ -676,7 +652,7 @@ static int set_row_vector(anml_model* m, const double* src, int on_device, const
     }
     CU_TRY(cudaMalloc(owned, (size_t)m->n_pad * sizeof(double)));
     CU_TRY(cudaMemset(*owned, 0, (size_t)m->n_pad * sizeof(double)));
-    if (m->n > 0) CU_TRY(cudaMemcpy(*owned, src, (size_t)m->n * sizeof(double), cudaMemcpyHostToDevice));
+    CU_TRY(upload_vector(m->device, 0, *owned, src, m->n));
     *view = *owned;
     return ANML_OK;
 }

@@ -254,17 +254,25 @@ __global__ void __launch_bounds__(256) add_priors_kernel(const PriorArgs a) {
 
 // Column validators on the device (reference: src/anml/data/validator.py:21-34):
 // flags[c] |= 1 if column c holds a NaN, |= 2 if it holds a value <= 0.
+// A thread keeps one column (consecutive threads = consecutive columns of a row, so the loads
+// coalesce) and ORs its findings in a register: one atomic per thread at the end, not one per
+// offending element (half of a standard-normal column is <= 0).
 __global__ void __launch_bounds__(256) validate_columns_kernel(const double* __restrict__ X, long long n, long long ld, int col0,
                                                                int ncols, int* __restrict__ flags) {
-    const long long total = n * ncols;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const long long i = e / ncols;
-        const int c = (int)(e - i * ncols);
-        const double v = X[i * ld + col0 + c];
+    for (int cbase = 0; cbase < ncols; cbase += 256) {
+        const int cw = ncols - cbase < 256 ? ncols - cbase : 256;
+        const int rows_per_pass = 256 / cw;
+        const int c = threadIdx.x % cw, rsub = threadIdx.x / cw;
         int f = 0;
-        if (v != v) f |= 1;
-        if (v <= 0.0) f |= 2;
-        if (f) atomicOr(flags + c, f);
+        if (rsub < rows_per_pass) {
+            const double* col = X + col0 + cbase + c;
+            for (long long i = (long long)blockIdx.x * rows_per_pass + rsub; i < n; i += (long long)gridDim.x * rows_per_pass) {
+                const double v = col[i * ld];
+                if (v != v) f |= 1;
+                if (v <= 0.0) f |= 2;
+            }
+        }
+        if (f) atomicOr(flags + cbase + c, f);
     }
 }
 
