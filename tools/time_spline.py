@@ -18,3 +18,23 @@ for _ in range(5):
     t0 = time.perf_counter(); d.set_spline(0, None, knots, deg, x_dev_ptr=xs.data_ptr()); ts.append(time.perf_counter() - t0)
 t = min(ts)
 print(json.dumps({"n": n, "nb": nb, "build_ms": t * 1e3, "write_GBps": n * nb * 8 / t / 1e9, "rows_per_s": n / t}))
+
+# config #3 evaluation on the dense 22-column design built above: gaussian NLL, identity link
+obs = torch.sin(2 * np.pi * xs) + 0.1 * torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+se = torch.ones(n, dtype=torch.float64, device="cuda")
+m = N.NativeModel(n, "gaussian", 1)
+m.set_param(0, d, N.LINK_CODES["Identity"])
+m.set_obs(dev_ptr=obs.data_ptr(), keepalive=obs); m.set_obs_se(dev_ptr=se.data_ptr(), keepalive=se)
+x = np.linspace(-1, 1, nb)
+for _ in range(3): m.eval(x)
+m.kernel_time(reset=True)
+t0 = time.perf_counter()
+for _ in range(10): o, gr, H = m.eval(x)
+e2e = (time.perf_counter() - t0) / 10 * 1e3
+kms, nl, al = m.kernel_time(reset=True)
+t0 = time.perf_counter()
+for _ in range(10): m.eval(x, N.WANT_OBJ | N.WANT_GRAD)
+e2e_g = (time.perf_counter() - t0) / 10 * 1e3
+band = int(np.max(np.abs(np.subtract.outer(np.arange(nb), np.arange(nb)))[H != 0]))
+print(json.dumps({"eval_ms": e2e, "main_kernel_ms": kms / 10, "objgrad_ms": e2e_g, "bytes_dense_GB": n * (nb + 2) * 8 / 1e9,
+                  "dense_GBps": n * (nb + 2) * 8 / (kms / 10) / 1e6, "hessian_bandwidth": band}))
