@@ -47,6 +47,8 @@ SIGNATURES = {
     "anml_design_download": (C.c_int, [C.c_void_p, _c_double_p, C.c_int64]),
     "anml_design_params": (C.c_int, [C.c_void_p, _c_double_p, C.c_void_p, C.c_int, C.c_int, _c_double_p]),
     "anml_spline_design": (C.c_int, [C.c_int, _c_double_p, C.c_int64, _c_double_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _c_double_p, _c_int32_p]),
+    "anml_vector_minmax": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int, _c_double_p, _c_double_p, C.POINTER(C.c_int)]),
+    "anml_vector_order_stats": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_int64), C.c_int, _c_double_p]),
     "anml_model_create": (C.c_int, [C.c_int, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "anml_model_destroy": (C.c_int, [C.c_void_p]),
     "anml_model_set_param": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
@@ -203,7 +205,7 @@ class Design:
         idx = np.empty(self.n_rows, dtype=np.int32) if want_index else None
         idx_p = idx.ctypes.data_as(_c_int32_p) if want_index else None
         if x_dev_ptr is not None:
-            xp, on_dev = C.c_void_p(int(x_dev_ptr)), 1
+            xp, on_dev = _as_ptr(x_dev_ptr), 1
         else:
             x = as_f64(x, "x")
             if x.size != self.n_rows:
@@ -260,6 +262,80 @@ def spline_design(x, knots, degree, ldegree=0, rdegree=0, order=0, want_index=Fa
                                     int(rdegree or 0), int(order), dptr(out),
                                     idx.ctypes.data_as(_c_int32_p) if want_index else None))
     return (out, idx) if want_index else out
+
+
+def _as_ptr(p) -> C.c_void_p:
+    """A device address given as an int, a ``c_void_p`` or a ``DeviceBuffer``."""
+    if isinstance(p, DeviceBuffer):
+        p = p.ptr
+    if isinstance(p, C.c_void_p):
+        return p
+    return C.c_void_p(int(p))
+
+
+def _vector_arg(x, dev_ptr, n):
+    if dev_ptr is not None:
+        return _as_ptr(dev_ptr), int(n), 1, None
+    x = as_f64(np.asarray(x).ravel(), "x")
+    return x.ctypes.data_as(C.c_void_p), x.size, 0, x
+
+
+def vector_minmax(x=None, dev_ptr=None, n=None, device=0):
+    """(min, max) of a host vector or of ``n`` doubles at ``dev_ptr``, reduced on the
+    device; NaN anywhere gives (nan, nan) like ``ndarray.min()/max()``."""
+    require_device(device)
+    xp, n, on_dev, keep = _vector_arg(x, dev_ptr, n)
+    if n == 0:
+        raise ValueError("zero-size array to reduction operation minimum which has no identity")
+    lo, hi, nan = C.c_double(), C.c_double(), C.c_int()
+    check(load().anml_vector_minmax(device, xp, n, on_dev, C.byref(lo), C.byref(hi), C.byref(nan)))
+    if nan.value:
+        return float("nan"), float("nan")
+    return lo.value, hi.value
+
+
+def vector_order_stats(ranks, x=None, dev_ptr=None, n=None, device=0) -> np.ndarray:
+    """``sorted(x)[ranks]`` from a device radix sort."""
+    require_device(device)
+    xp, n, on_dev, keep = _vector_arg(x, dev_ptr, n)
+    ranks = np.ascontiguousarray(ranks, dtype=np.int64).ravel()
+    out = np.empty(ranks.size, dtype=np.float64)
+    if ranks.size:
+        check(load().anml_vector_order_stats(device, xp, n, on_dev, ranks.ctypes.data_as(C.POINTER(C.c_int64)), ranks.size, dptr(out)))
+    return out
+
+
+def vector_quantile(q, x=None, dev_ptr=None, n=None, device=0) -> np.ndarray:
+    """``np.quantile(x, q)`` (default ``method="linear"``): the order statistics come from
+    the device sort, the interpolation is NumPy's own formula on the host
+    (numpy/lib/_function_base_impl.py: virtual index ``(n-1)*q``, ``_get_indexes``,
+    ``_lerp``), so the result carries the same bits."""
+    q = np.asarray(q, dtype=np.float64)
+    if q.size and not (np.all(q >= 0) and np.all(q <= 1)):
+        raise ValueError("Quantiles must be in the range [0, 1]")
+    if dev_ptr is None:
+        x = as_f64(np.asarray(x).ravel(), "x")
+        n = x.size
+    n = int(n)
+    if n == 0:
+        raise IndexError("index -1 is out of bounds for axis 0 with size 0")
+    lo, hi = vector_minmax(x, dev_ptr, n, device)
+    if lo != lo:  # NaNs sort to the end and poison every quantile
+        return np.full(q.shape, np.nan)
+    vi = (n - 1) * q.ravel()
+    prev = np.floor(vi)
+    nxt = prev + 1
+    above = vi >= n - 1
+    prev[above] = n - 1
+    nxt[above] = n - 1
+    ranks = np.concatenate([prev, nxt]).astype(np.int64)
+    vals = vector_order_stats(ranks, x, dev_ptr, n, device)
+    a, b = vals[: vi.size], vals[vi.size:]
+    t = vi - np.where(above, -1.0, np.floor(vi))  # NumPy's gamma uses the wrapped index -1 there; a == b, so it is inert
+    diff = np.subtract(b, a)
+    out = np.add(a, diff * t)
+    np.subtract(b, diff * (1 - t), out=out, where=t >= 0.5)
+    return out.reshape(q.shape)
 
 
 class NativeModel:

@@ -2,6 +2,7 @@
 // descriptors, kernel dispatch.  Host-side only; kernels live in the .cuh files.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <cmath>
 #include <cstdarg>
@@ -348,6 +349,122 @@ extern "C" int anml_design_validate_columns(const anml_design* d, int col0, int 
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
         return fail(ANML_ECUDA, "anml_design_validate_columns: %s", cudaGetErrorString(e));
+    }
+    return ANML_OK;
+}
+
+// ----------------------------------------------------------------------------
+// knot placement from data (getter/spline.py:92-99)
+// ----------------------------------------------------------------------------
+static int device_sm_count(int device, int* out) {
+    CU_TRY(cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, device));
+    return ANML_OK;
+}
+
+// x on the device: either the caller's pointer or an uploaded copy (freed by the caller through *owned)
+static int vector_on_device(int device, int sm_count, const double* x, int64_t n, int on_device, const double** view, double** owned) {
+    *owned = nullptr;
+    if (on_device) {
+        *view = x;
+        return ANML_OK;
+    }
+    CU_TRY(cudaMalloc(owned, (size_t)n * sizeof(double)));
+    const cudaError_t e = upload_vector(device, sm_count, *owned, x, n);
+    if (e != cudaSuccess) {
+        cudaFree(*owned);
+        *owned = nullptr;
+        (void)cudaGetLastError();
+        return fail(ANML_ECUDA, "upload failed: %s", cudaGetErrorString(e));
+    }
+    *view = *owned;
+    return ANML_OK;
+}
+
+extern "C" int anml_vector_minmax(int device, const double* x, int64_t n, int x_on_device, double* out_min, double* out_max, int* has_nan) {
+    if (!x || !out_min || !out_max || !has_nan) return fail(ANML_EINVAL, "anml_vector_minmax: NULL argument");
+    if (n <= 0) return fail(ANML_EINVAL, "anml_vector_minmax: zero-size array has no minimum");
+    CU_TRY(cudaSetDevice(device));
+    int sms = 0;
+    TRY(device_sm_count(device, &sms));
+    const double* xd = nullptr;
+    double* owned = nullptr;
+    TRY(vector_on_device(device, sms, x, n, x_on_device, &xd, &owned));
+    const int grid = grid_for(n, 256, sms, 8);
+    double* part = nullptr;
+    cudaError_t e = cudaMalloc(&part, (size_t)grid * (2 * sizeof(double) + sizeof(int)));
+    std::vector<double> hmin(grid), hmax(grid);
+    std::vector<int> hnan(grid);
+    if (e == cudaSuccess) {
+        double* pmin = part;
+        double* pmax = part + grid;
+        int* pnan = reinterpret_cast<int*>(part + 2 * (size_t)grid);
+        minmax_kernel<<<grid, 256>>>(xd, n, pmin, pmax, pnan);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpy(hmin.data(), pmin, grid * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(hmax.data(), pmax, grid * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(hnan.data(), pnan, grid * sizeof(int), cudaMemcpyDeviceToHost);
+    }
+    if (part) cudaFree(part);
+    if (owned) cudaFree(owned);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(ANML_ECUDA, "anml_vector_minmax: %s", cudaGetErrorString(e));
+    }
+    double lo = hmin[0], hi = hmax[0];
+    int nan = hnan[0];
+    for (int b = 1; b < grid; ++b) {
+        lo = std::fmin(lo, hmin[b]);
+        hi = std::fmax(hi, hmax[b]);
+        nan |= hnan[b];
+    }
+    *out_min = lo;
+    *out_max = hi;
+    *has_nan = nan;
+    return ANML_OK;
+}
+
+extern "C" int anml_vector_order_stats(int device, const double* x, int64_t n, int x_on_device, const int64_t* ranks, int n_ranks,
+                                       double* out) {
+    if (!x || !ranks || !out || n_ranks <= 0) return fail(ANML_EINVAL, "anml_vector_order_stats: bad arguments");
+    if (n <= 0) return fail(ANML_EINVAL, "anml_vector_order_stats: empty vector");
+    if (n > 2147483000LL) return fail(ANML_EUNSUPPORTED, "anml_vector_order_stats: at most 2^31 values");
+    for (int i = 0; i < n_ranks; ++i)
+        if (ranks[i] < 0 || ranks[i] >= n) return fail(ANML_EINVAL, "anml_vector_order_stats: rank %lld outside [0, %lld)", (long long)ranks[i], (long long)n);
+    CU_TRY(cudaSetDevice(device));
+    int sms = 0;
+    TRY(device_sm_count(device, &sms));
+    const double* xd = nullptr;
+    double* owned = nullptr;
+    TRY(vector_on_device(device, sms, x, n, x_on_device, &xd, &owned));
+    double* sorted = nullptr;
+    void* temp = nullptr;
+    long long* ranks_dev = nullptr;
+    double* out_dev = nullptr;
+    size_t temp_bytes = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, xd, sorted, (int)n);
+    if (e == cudaSuccess) e = cudaMalloc(&sorted, (size_t)n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&temp, temp_bytes ? temp_bytes : 16);
+    if (e == cudaSuccess) e = cudaMalloc(&ranks_dev, (size_t)n_ranks * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMalloc(&out_dev, (size_t)n_ranks * sizeof(double));
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortKeys(temp, temp_bytes, xd, sorted, (int)n);
+    if (e == cudaSuccess) {
+        static_assert(sizeof(long long) == sizeof(int64_t), "rank type");
+        e = cudaMemcpy(ranks_dev, ranks, (size_t)n_ranks * sizeof(long long), cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) {
+        gather_kernel<<<(n_ranks + 127) / 128, 128>>>(sorted, ranks_dev, n_ranks, out_dev);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, out_dev, (size_t)n_ranks * sizeof(double), cudaMemcpyDeviceToHost);
+    const int code = (e == cudaErrorMemoryAllocation) ? ANML_ENOMEM : ANML_ECUDA;
+    if (sorted) cudaFree(sorted);
+    if (temp) cudaFree(temp);
+    if (ranks_dev) cudaFree(ranks_dev);
+    if (out_dev) cudaFree(out_dev);
+    if (owned) cudaFree(owned);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(code, "anml_vector_order_stats: %s", cudaGetErrorString(e));
     }
     return ANML_OK;
 }

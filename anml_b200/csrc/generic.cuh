@@ -6,6 +6,7 @@
 //   add_priors_kernel  Gaussian prior terms on the packed result
 // All are HBM-bound: coalesced 16-byte loads, fixed-order reductions.
 #pragma once
+#include <math_constants.h>
 #include "common.cuh"
 #include "rowmath.cuh"
 
@@ -274,6 +275,49 @@ __global__ void __launch_bounds__(256) validate_columns_kernel(const double* __r
         }
         if (f) atomicOr(flags + cbase + c, f);
     }
+}
+
+// per-block (min, max, saw-a-NaN) of a vector; the few hundred block records are finished on the host
+__global__ void __launch_bounds__(256) minmax_kernel(const double* __restrict__ x, long long n, double* __restrict__ block_min,
+                                                     double* __restrict__ block_max, int* __restrict__ block_nan) {
+    double lo = CUDART_INF, hi = -CUDART_INF;
+    int nan = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = x[i];
+        nan |= (v != v);
+        lo = fmin(lo, v);
+        hi = fmax(hi, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        nan |= __shfl_xor_sync(0xffffffffu, nan, o);
+    }
+    __shared__ double s_lo[8], s_hi[8];
+    __shared__ int s_nan[8];
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        s_lo[w] = lo;
+        s_hi[w] = hi;
+        s_nan[w] = nan;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) {
+            lo = fmin(lo, s_lo[k]);
+            hi = fmax(hi, s_hi[k]);
+            nan |= s_nan[k];
+        }
+        block_min[blockIdx.x] = lo;
+        block_max[blockIdx.x] = hi;
+        block_nan[blockIdx.x] = nan;
+    }
+}
+
+__global__ void gather_kernel(const double* __restrict__ sorted, const long long* __restrict__ ranks, int n_ranks, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_ranks) out[i] = sorted[ranks[i]];
 }
 
 __global__ void fill_kernel(double* p, long long n, double v) {

@@ -55,5 +55,22 @@ class SplineGetter:
             return lo + self.knots * (hi - lo)
         return np.quantile(data, self.knots)
 
+    def resolve_knots_device(self, dev_ptr: int, n: int, device: int = 0) -> NDArray:
+        """``resolve_knots`` for ``n`` abscissae that already sit in device memory: the
+        min/max pass or the sort behind the quantiles runs there (same values as the
+        host route: min/max are exact, the quantile interpolation is NumPy's formula)."""
+        from .. import _native
+
+        if self.knots_type == "abs":
+            return self.knots
+        if self.knots_type == "rel_domain":
+            lo, hi = _native.vector_minmax(dev_ptr=dev_ptr, n=n, device=device)
+            lo, hi = np.float64(lo), np.float64(hi)
+            return lo + self.knots * (hi - lo)
+        return _native.vector_quantile(self.knots, dev_ptr=dev_ptr, n=n, device=device)
+
+    def get_spline_device(self, dev_ptr: int, n: int, device: int = 0) -> XSpline:
+        return XSpline(self.resolve_knots_device(dev_ptr, n, device), self.degree, ldegree=self.ldegree, rdegree=self.rdegree)
+
     def get_spline(self, data: NDArray) -> XSpline:
         return XSpline(self.resolve_knots(data), self.degree, ldegree=self.ldegree, rdegree=self.rdegree)

@@ -139,9 +139,10 @@ class Parameter:
             self.offset.attach(df)
             self._offset_dev = _native.DeviceBuffer(self.device, np.asarray(self.offset.value, dtype=np.float64))
         # sizes can depend on the first attach of a spline variable, so resolve those first;
-        # plain variables attach inside _write_design (validators run on the device)
+        # plain variables attach inside _write_design (validators run on the device), spline
+        # variables too (their size is known from the getter; knots are resolved from the device copy)
         for v in self.variables:
-            if type(v) is not Variable:
+            if type(v) is not Variable and not getattr(v, "_resolves_on_device", False):
                 v.attach(df)
         design = _native.Design(n, self.size, self.device)
         col = 0

@@ -16,6 +16,9 @@ from .main import Variable
 
 SplineVariablePrior = Union[Prior, SplinePriorGetter]
 
+# below this many rows NumPy resolves data-dependent knots faster than a device round trip
+_DEVICE_KNOTS_MIN_ROWS = 1 << 16
+
 
 class SplineVariable(Variable):
     """``spline`` is an ``XSpline`` or a ``SplineGetter``; the getter becomes an
@@ -24,6 +27,7 @@ class SplineVariable(Variable):
     (spline.py:103-107)."""
 
     _prior_types: Tuple[Type, ...] = (Prior, SplinePriorGetter)
+    _resolves_on_device = True  # Parameter.attach leaves the first attach to _write_design
 
     def __init__(self, component: Union[str, Component], spline: Union[XSpline, SplineGetter],
                  priors: Optional[List[SplineVariablePrior]] = None):
@@ -68,9 +72,26 @@ class SplineVariable(Variable):
         return False, False  # the component's validators already ran on the host column in attach()
 
     def _write_design(self, design, col0: int, df: DataFrame) -> None:
-        self.attach(df)
-        sp = self.spline
-        if sp.num_spline_bases != self.size:
-            raise NotImplementedError("ldegree/rdegree that change the basis count are not supported")
-        self.last_interval_index = design.set_spline(col0, self.component.value, sp.knots, sp.degree, sp.ldegree or 0,
-                                                     sp.rdegree or 0, 0, want_index=False)
+        """Upload the abscissae once; knots that depend on the data (first attach of a
+        ``SplineGetter``) are resolved from that device copy, then the basis is built from it."""
+        from .. import _native
+
+        self.component.attach(df)
+        x = _native.as_f64(self.component.value, self.component.key)
+        xbuf = _native.DeviceBuffer(design.device, x)
+        try:
+            if isinstance(self.spline, SplineGetter):
+                if x.size >= _DEVICE_KNOTS_MIN_ROWS:
+                    self.spline = self.spline.get_spline_device(xbuf.ptr, x.size, design.device)
+                else:
+                    self.spline = self.spline.get_spline(x)
+            for i, prior in enumerate(self.priors):
+                if isinstance(prior, SplinePriorGetter):
+                    self.priors[i] = prior.get_prior(self.spline)
+            sp = self.spline
+            if sp.num_spline_bases != self.size:
+                raise NotImplementedError("ldegree/rdegree that change the basis count are not supported")
+            self.last_interval_index = design.set_spline(col0, None, sp.knots, sp.degree, sp.ldegree or 0, sp.rdegree or 0, 0,
+                                                         want_index=False, x_dev_ptr=xbuf.ptr)
+        finally:
+            xbuf.free()

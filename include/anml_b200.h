@@ -107,6 +107,16 @@ int anml_design_params(const anml_design* d, const double* beta_host, const doub
 int anml_spline_design(int device, const double* x_host, int64_t n, const double* knots, int n_knots, int degree,
                        int ldegree, int rdegree, int order, double* out_host, int32_t* interval_out);
 
+/* ---- knot placement from data (SplineGetter.get_spline, getter/spline.py:92-99) ----
+ * 'rel_domain' knots need data.min()/max(), 'rel_freq' knots np.quantile(data, k): one pass /
+ * one sort over the n abscissae, done on the device that already holds them.
+ * minmax: NaN anywhere -> *has_nan = 1 (NumPy then returns nan for both).
+ * order_stats: out[i] = sorted(x)[ranks[i]], 0 <= ranks[i] < n (the order statistics
+ * np.quantile interpolates between; the interpolation itself stays on the host). */
+int anml_vector_minmax(int device, const double* x, int64_t n, int x_on_device, double* out_min, double* out_max, int* has_nan);
+int anml_vector_order_stats(int device, const double* x, int64_t n, int x_on_device, const int64_t* ranks, int n_ranks,
+                            double* out);
+
 /* ---- model: objective / gradient / Hessian ---------------- */
 int anml_model_create(int device, int64_t n_rows, int family, int n_params, anml_model** out);
 int anml_model_destroy(anml_model* m);

@@ -86,3 +86,67 @@ def test_spline_argument_errors():
         _native.spline_design([0.5], [0.0, 1.0], 9)  # degree above the kernel's limit
     out = _native.spline_design(np.empty(0), [0.0, 1.0], 3)
     assert out.shape == (0, 4)
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 100_003, (1 << 20) + 3])
+def test_device_minmax_and_quantiles_carry_numpy_bits(n):
+    """Knot placement from data (getter/spline.py:92-99): data.min()/max() and
+    np.quantile(data, k) recomputed on the device are the same doubles."""
+    from anml_b200 import _native as N
+
+    rng = np.random.default_rng(n)
+    x = rng.normal(size=n) * 3.0
+    if n > 10:
+        x[: n // 3] = np.round(x[: n // 3], 1)  # plenty of ties
+    q = np.concatenate([np.linspace(0.0, 1.0, 20), [0.5, 1.0 / 3.0, 0.999999, 1e-9]])
+    lo, hi = N.vector_minmax(x)
+    assert lo == x.min() and hi == x.max()
+    got = N.vector_quantile(q, x)
+    want = np.quantile(x, q)
+    np.testing.assert_array_equal(got, want)
+    # same through a device-resident copy
+    buf = N.DeviceBuffer(0, x)
+    np.testing.assert_array_equal(N.vector_quantile(q, dev_ptr=buf.ptr, n=n), want)
+    assert N.vector_minmax(dev_ptr=buf.ptr, n=n) == (x.min(), x.max())
+    # order statistics themselves
+    ranks = np.unique(rng.integers(0, n, size=min(n, 50)))
+    np.testing.assert_array_equal(N.vector_order_stats(ranks, x), np.sort(x)[ranks])
+
+
+def test_device_minmax_and_quantiles_with_nan_and_errors():
+    from anml_b200 import _native as N
+
+    x = np.array([1.0, np.nan, -2.0, 5.0])
+    lo, hi = N.vector_minmax(x)
+    assert np.isnan(lo) and np.isnan(hi)
+    assert np.isnan(N.vector_quantile([0.0, 0.5], x)).all() and np.isnan(np.quantile(x, [0.0, 0.5])).all()
+    with pytest.raises(ValueError):
+        N.vector_minmax(np.empty(0))
+    with pytest.raises(ValueError):
+        N.vector_quantile([1.5], np.arange(4.0))
+
+
+@pytest.mark.parametrize("knots_type", ["rel_domain", "rel_freq"])
+def test_spline_variable_resolves_data_dependent_knots_on_device(knots_type):
+    """Above 65536 rows SplineVariable places rel_domain / rel_freq knots from the
+    uploaded abscissae; they equal the host rule bit for bit and the basis follows."""
+    import pandas as pd
+
+    from anml_b200.getter.spline import SplineGetter
+    from anml_b200.parameter import Parameter
+    from anml_b200.variable import SplineVariable
+
+    rng = np.random.default_rng(8)
+    n = 150_001
+    x = rng.gamma(2.0, 1.5, size=n)
+    df = pd.DataFrame({"x": x})
+    fractions = np.linspace(0.0, 1.0, 9)
+    getter = SplineGetter(fractions, degree=3, knots_type=knots_type)
+    want_knots = getter.resolve_knots(x)
+    var = SplineVariable("x", getter)
+    par = Parameter([var])
+    par.attach(df)
+    np.testing.assert_array_equal(var.spline.knots, want_knots)
+    assert par.size == 11 and par.design_mat.shape == (n, 11)
+    want = O.spline_design(want_knots, 3, x)
+    np.testing.assert_array_equal(par.design_mat, want)
