@@ -32,7 +32,7 @@ struct UploadPool {
 };
 
 constexpr long long UPLOAD_LANE_ELEMS = 1LL << 21;      // 16 MiB of doubles per lane
-constexpr long long UPLOAD_INLINE_ELEMS = 1LL << 20;    // below 8 MiB: calling thread only
+constexpr long long UPLOAD_INLINE_ELEMS = 1LL << 18;    // up to 2 MiB: calling thread only
 constexpr int UPLOAD_MAX_DEVICES = 64;
 
 static UploadPool g_upload_pools[UPLOAD_MAX_DEVICES];
