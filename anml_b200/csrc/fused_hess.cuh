@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
         if (NHELP == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_H));
         const int hid = role - 1;  // handles the team's blocks i with (i % HELPERS) == hid
         double objacc = 0.0;
+        LogProduct logprod;
         double gacc[NB8];
 #pragma unroll
         for (int i = 0; i < NB8; ++i) gacc[i] = 0.0;
@@ -313,16 +314,20 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
                     y = transpose_reduce8(part, g);
                 }
                 if (valid) {
-                    const RowTerms1 rt = row_terms1<true>(a.family, a.link, (a.fast & 1) != 0, y + off, ob, se);
-                    bad_domain |= !rt.ok;
                     if (a.weights) {  // per-row likelihood weight (>= 0): scales l, r, w
+                        const RowTerms1 rt = row_terms1<true>(a.family, a.link, (a.fast & 1) != 0, y + off, ob, se);
+                        bad_domain |= !rt.ok;
                         const double wt = a.weights[row];
                         objacc += wt * rt.l;
                         rr = wt * rt.r;
                         ww = wt * rt.w;
                         sc = sqrt(wt) * rt.sw;
                     } else {
+                        // the logistic log(1 + e^-y) terms are multiplied up and logged once at the end
+                        const RowTerms1 rt = row_terms1<true, true>(a.family, a.link, (a.fast & 1) != 0, y + off, ob, se);
+                        bad_domain |= !rt.ok;
                         objacc += rt.l;
+                        logprod.mul(rt.ls);
                         rr = rt.r;
                         ww = rt.w;
                         sc = rt.sw;
@@ -366,7 +371,7 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
             const uint32_t hb = hrec_base + (team * C::HELPERS + hid) * (NB8 + 1) * 256;
 #pragma unroll
             for (int jb = 0; jb < NB8; ++jb) sts64(hb + (jb * 32 + lane) * 8, gacc[jb]);
-            sts64(hb + (NB8 * 32 + lane) * 8, objacc);
+            sts64(hb + (NB8 * 32 + lane) * 8, objacc + logprod.log_value());
         }
         asm volatile("bar.sync 1, %0;" ::"n"(C::THREADS) : "memory");
     }

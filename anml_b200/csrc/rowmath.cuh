@@ -63,14 +63,20 @@ __device__ __forceinline__ double link_order(int link, double y, int order, bool
 struct RowTerms1 {
     double l, r, w;
     double sw;  // sqrt(|w|), filled only when asked for
+    double ls;  // DEFER_LOG only: the row's NLL term is l + log(ls) (1.0 when nothing is deferred)
     bool ok;
 };
 
-template <bool WANT_SQRT = false>
+// DEFER_LOG: the canonical logistic term log(1 + e^-y) is not evaluated per row; the caller multiplies
+// the returned factors ls = 1 + e^-y into a running product (LogProduct below) and takes ONE log at the
+// end.  In the warp-specialised Hessian kernel every FP64 instruction of a helper warp has to squeeze into
+// the DMMA stream, and libdevice's log is 22 of them per row.
+template <bool WANT_SQRT = false, bool DEFER_LOG = false>
 __device__ __forceinline__ RowTerms1 row_terms1(int family, int link, bool fast, double y, double obs, double se) {
     RowTerms1 o;
     o.ok = true;
     o.sw = 0.0;
+    o.ls = 1.0;
     if (fast && family == FAM_BINOMIAL && link == LINK_EXPIT) {
         // canonical logistic: one exp, one log, one reciprocal per row.
         // h = exp(-y/2): z = h^2 and sqrt(w) = h q come for free (no sqrt).
@@ -78,7 +84,12 @@ __device__ __forceinline__ RowTerms1 row_terms1(int family, int link, bool fast,
         const double z = h * h;
         const double s = 1.0 + z;
         const double q = 1.0 / s;
-        o.l = log(s) + (1.0 - obs) * y;
+        if (DEFER_LOG) {
+            o.ls = s;
+            o.l = (1.0 - obs) * y;
+        } else {
+            o.l = log(s) + (1.0 - obs) * y;
+        }
         o.r = q - obs;
         o.sw = h * q;
         o.w = o.sw * o.sw;
@@ -129,6 +140,26 @@ __device__ __forceinline__ RowTerms1 row_terms1(int family, int link, bool fast,
     if (WANT_SQRT) o.sw = sqrt(fabs(o.w));
     return o;
 }
+
+// Running product of factors >= 1 kept as mantissa in [1, 2) x 2^exponent: sum_i log(f_i) =
+// exponent * ln 2 + log(mantissa).  One DMUL per factor; the renormalisation is integer work on the
+// exponent field.  Relative rounding error grows like sqrt(#factors) * 2^-53 on the mantissa, i.e. an
+// ABSOLUTE error of ~1e-14 on a sum of thousands of logs -- tighter than adding rounded logs.  A factor
+// that is inf or NaN (exponent field 0x7ff) stays in the mantissa and poisons the result like log would.
+struct LogProduct {
+    double mant = 1.0;
+    int expo = 0;  // < 1075 per factor: no overflow below 2e6 factors per lane
+    __device__ __forceinline__ void mul(double f) {
+        mant *= f;
+        const int hi = __double2hiint(mant);
+        const int ef = (hi >> 20) & 0x7ff;
+        if (ef != 0x7ff) {
+            expo += ef - 1023;
+            mant = __hiloint2double(hi - ((ef - 1023) << 20), __double2loint(mant));
+        }
+    }
+    __device__ __forceinline__ double log_value() const { return (double)expo * 0.6931471805599453094 + log(mant); }
+};
 
 // Two-parameter Gaussian (mean mu = f0(y0), variance v = f1(y1)):
 //   l = 1/2 log v + 1/2 (obs-mu)^2 / v

@@ -52,7 +52,8 @@ def gpu_eval(family, X, obs, se, off, link, x, prior=None, options=()):
         model.set_option(name, val)
     out = model.eval(x)
     out2 = model.eval(x)  # determinism: bitwise identical on repeat
-    assert out[0] == out2[0] and np.array_equal(out[1], out2[1]) and np.array_equal(out[2], out2[2])
+    assert np.array_equal(out[0], out2[0], equal_nan=True) and np.array_equal(out[1], out2[1], equal_nan=True)
+    assert np.array_equal(out[2], out2[2], equal_nan=True)
     return out
 
 
@@ -238,3 +239,36 @@ def test_row_weights_scale_every_term(family, link, p):
         m.set_weights(-wts - 1.0)
     m.set_weights(None)  # back to unweighted
     check(m.eval(x), O.model_eval_fused(family, obs, [X], [link], x, offsets=[off]))
+
+
+def test_logistic_objective_product_accumulator_extremes():
+    """The Hessian kernel multiplies the factors 1 + e^-y of the logistic NLL and takes one
+    log at the end (rowmath.cuh LogProduct).  Wide linear predictors exercise the exponent
+    bookkeeping (|y| up to ~600: factors up to e^600), an overflowing row must give +inf and
+    a NaN row NaN, as the per-row log did."""
+    rng = np.random.default_rng(17)
+    n, p = 40_003, 8
+    X = rng.normal(size=(n, p))
+    X[:, 0] = 1.0
+    x = rng.normal(size=p)
+    x[1] = 150.0  # y spreads over +-600
+    y = X @ x
+    keep = np.abs(y) < 600.0
+    X, y = X[keep], y[keep]
+    obs = (rng.uniform(size=X.shape[0]) < 0.5).astype(float)
+    got = gpu_eval("binomial", X, obs, None, None, "expit", x)
+    # stable reference for the objective: log(1 + e^-y) = logaddexp(0, -y)
+    want_obj = np.logaddexp(0.0, -y).sum() + ((1.0 - obs) * y).sum()
+    assert np.isfinite(got[0]) and abs(got[0] - want_obj) <= 1e-12 * abs(want_obj)
+    q = 1.0 / (1.0 + np.exp(-y))
+    want_g = X.T @ (q - obs)
+    assert np.abs(got[1] - want_g).max() <= 1e-10 * np.abs(want_g).max()
+
+    Xo = X[:1000].copy()
+    Xo[5, 1] = -20.0  # y ~ -3000: e^-y overflows
+    got = gpu_eval("binomial", Xo, obs[:1000], None, None, "expit", x)
+    assert got[0] == np.inf
+    Xn = X[:1000].copy()
+    Xn[7, 2] = np.nan
+    got = gpu_eval("binomial", Xn, obs[:1000], None, None, "expit", x)
+    assert np.isnan(got[0])
