@@ -69,6 +69,8 @@ struct anml_design {
     bool owned = false;
     CUtensorMap tmap;    // box 16 rows x 16 cols, 128B swizzle
     CUtensorMap tmap32;  // box 32 rows x 16 cols, 128B swizzle
+    CUtensorMap tmap3d;  // (16 cols, rows, 16-column groups), box 16 x 32 x p/16: one TMA per 32-row block (p % 16 == 0 only)
+    bool has3d = false;
     int sm_count = 0;
 };
 
@@ -215,6 +217,19 @@ static int encode_design_tmap(anml_design* d) {
     r = fn(&d->tmap32, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d->X, gdim, gstride, box32, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ANML_ECUDA, "cuTensorMapEncodeTiled (32-row box) failed with CUresult %d", (int)r);
+    memset(&d->tmap3d, 0, sizeof(d->tmap3d));
+    d->has3d = false;
+    if (d->p % 16 == 0 && d->p <= 64) {
+        // the whole 32-row block in one TMA instruction: dim2 walks the 16-column groups (stride 128 B),
+        // so shared memory gets [group][row][16 cols] = the layout of the per-group boxes
+        cuuint64_t gdim3[3] = {16, (cuuint64_t)d->n, (cuuint64_t)(d->p / 16)};
+        cuuint64_t gstride3[2] = {(cuuint64_t)d->ld * sizeof(double), 128};
+        cuuint32_t box3[3] = {16, 32, (cuuint32_t)(d->p / 16)};
+        cuuint32_t estride3[3] = {1, 1, 1};
+        r = fn(&d->tmap3d, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, d->X, gdim3, gstride3, box3, estride3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        d->has3d = (r == CUDA_SUCCESS);
+    }
     return ANML_OK;
 }
 
@@ -942,18 +957,25 @@ static int launch_fused_t(const anml_design* d, const FusedArgs& a, int grid, cu
     return ANML_OK;
 }
 
-template <int NB16, int NHELP, bool SIGNED, int MODE>
-static int launch_hess_t(const anml_design* d, const FusedArgs& a, int grid, cudaStream_t st) {
+template <int NB16, int NHELP, bool SIGNED, int MODE, bool TMA3D>
+static int launch_hess_tt(const anml_design* d, const FusedArgs& a, int grid, cudaStream_t st) {
     using C = HessCfg<NB16, NHELP>;
     static bool configured = false;
-    auto kern = fused_hess_kernel<NB16, NHELP, SIGNED, MODE>;
+    auto kern = fused_hess_kernel<NB16, NHELP, SIGNED, MODE, TMA3D>;
     if (!configured) {
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured = true;
     }
-    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(d->tmap32, a);
+    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(TMA3D ? d->tmap3d : d->tmap32, a);
     CU_TRY(cudaGetLastError());
     return ANML_OK;
+}
+
+template <int NB16, int NHELP, bool SIGNED, int MODE>
+static int launch_hess_t(const anml_design* d, const FusedArgs& a, int grid, cudaStream_t st) {
+    // one 3-D TMA per block when the width is a multiple of 16 (no partial column group)
+    if (d->has3d && d->p == 16 * NB16) return launch_hess_tt<NB16, NHELP, SIGNED, MODE, true>(d, a, grid, st);
+    return launch_hess_tt<NB16, NHELP, SIGNED, MODE, false>(d, a, grid, st);
 }
 
 // canonical link/family pairs have Hessian weights w > 0 (no sign handling in the tensor warp)

@@ -115,7 +115,9 @@ __device__ __forceinline__ void mma_kstep(double* acc, const double* av, uint32_
 
 // MODE 0: per-row terms computed here from X, beta, obs (one-parameter models);
 // MODE 1: (r, w) read from a.rvec / a.wvec (blocks of the general path).
-template <int NB16, int NHELP, bool SIGNED, int MODE>
+// TMA3D: the tensor map is the 3-D view (16 cols, rows, column groups) and one instruction
+// fetches the whole block (api.cu encodes it when p is a multiple of 16).
+template <int NB16, int NHELP, bool SIGNED, int MODE, bool TMA3D>
 __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const __grid_constant__ CUtensorMap tmap32, const FusedArgs a) {
     using C = HessCfg<NB16, NHELP>;
     constexpr int NB8 = C::NB8, NT = C::NT, NBUF = C::NBUF, TEAMS = C::TEAMS;
@@ -168,8 +170,12 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
             const uint32_t bar = full_u32 + buf * 8;
             const uint32_t dst = ring_u32 + buf * C::BUF_BYTES;
             mbar_arrive_expect_tx(bar, C::BUF_BYTES);
+            if (TMA3D) {
+                tma_load_3d(dst, &tmap32, 0, (int)row0, 0, bar);
+            } else {
 #pragma unroll
-            for (int j = 0; j < NB16; ++j) tma_load_2d(dst + j * 4096, &tmap32, 16 * j, (int)row0, bar);
+                for (int j = 0; j < NB16; ++j) tma_load_2d(dst + j * 4096, &tmap32, 16 * j, (int)row0, bar);
+            }
         };
         if (lane == 0) {
             const int pre = nmine < NBUF ? (int)nmine : NBUF;
