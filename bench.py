@@ -42,7 +42,7 @@ P = 64
 METRIC = "obj+grad+Hessian evals/sec at N=100M,p=64"
 UNIT = "evals/s"
 # dram bytes per row of the fused kernel from the ncu --set full capture in profiles/ (n = 1e7: 5.2136 GB, profiles/r1_fused_hess_kernel_ncu.csv)
-NCU_DRAM_BYTES_PER_ROW = 521.52
+NCU_DRAM_BYTES_PER_ROW = 521.20
 
 
 def workload_name(n_total, p):
