@@ -11,6 +11,7 @@ from typing import Any, List, Optional
 
 from pandas import DataFrame
 
+from .frame import as_frame
 from .validator import Validator
 
 
@@ -66,6 +67,7 @@ class Component:
         """Fetch, validate and cache the column.  ``skip`` names validator classes the
         caller will run itself (``Parameter.attach`` runs ``NoNans`` / ``Positive`` on the
         device after the upload instead of scanning the column on the host)."""
+        df = as_frame(df)
         if self.key not in df:
             if self.default_value is None:
                 raise KeyError(f"Dataframe doesn't contain column {self.key}.")

@@ -24,6 +24,7 @@ import numpy as np
 from pandas import DataFrame
 from scipy.linalg import block_diag
 
+from .data.frame import as_frame
 from . import _native
 from .data.example import DataExample
 from .data.prototype import DataPrototype
@@ -85,6 +86,7 @@ class Model:
         """Attach observations and every parameter (design matrices go to the
         GPU), then configure the native model."""
         _native.require_device(self.device)
+        df = as_frame(df)
         self.data.attach(df)
         first = self.parameters[0]
         first.attach(df)

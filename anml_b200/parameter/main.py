@@ -24,6 +24,7 @@ from numpy.typing import NDArray
 from pandas import DataFrame
 from scipy.linalg import block_diag
 
+from ..data.frame import as_frame
 from .. import _native
 from ..data.component import Component
 from ..data.validator import NoNans
@@ -133,6 +134,7 @@ class Parameter:
         """Cache offset, design matrix (on the device) and the four combined
         priors; rebuilt on every call like the reference (main.py:148-165)."""
         _native.require_device(self.device)
+        df = as_frame(df)  # pandas frame, or a pyarrow.Table behind the same few methods
         n = len(df)
         self._offset_dev = None
         if self.offset is not None:

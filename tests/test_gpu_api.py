@@ -360,3 +360,35 @@ def test_upload_paths_round_trip_exactly(threads, monkeypatch):
     C3 = rng.standard_normal((100_001, 3))
     d3.set_columns(0, C3)
     assert np.array_equal(d3.download(), C3)
+
+
+@pytest.mark.gpu
+def test_attach_from_pyarrow_table_equals_attach_from_pandas():
+    pa = pytest.importorskip("pyarrow")
+    import pandas as pd
+
+    from anml_b200.data import Component, DataExample
+    from anml_b200.model import Model
+    from anml_b200.parameter import Expit, Parameter
+    from anml_b200.variable import Variable
+
+    rng = np.random.default_rng(21)
+    n = 30_011
+    cols = {f"c{j}": rng.normal(size=n) for j in range(1, 6)}
+    cols["obs"] = (rng.uniform(size=n) < 0.4).astype(float)
+    x = rng.normal(size=6) * 0.2
+
+    def build():
+        par = Parameter([Variable(Component("intercept", default_value=1.0))] + [Variable(f"c{j}") for j in range(1, 6)], transform=Expit())
+        return par, Model("binomial", DataExample("obs", "obs_se"), [par])
+
+    par_pd, model_pd = build()
+    model_pd.attach(pd.DataFrame(cols))
+    par_pa, model_pa = build()
+    table = pa.table(cols)
+    model_pa.attach(table)
+    assert table.column_names == list(cols)  # the immutable table is left alone
+    np.testing.assert_array_equal(par_pa.design_mat, par_pd.design_mat)
+    a, b = model_pd.evaluate(x), model_pa.evaluate(x)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    np.testing.assert_array_equal(par_pa.get_params(x, table), par_pd.get_params(x))

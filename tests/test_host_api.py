@@ -285,3 +285,32 @@ def test_spline_prior_getter_contract():
     with pytest.raises(TypeError):
         g.get_prior("not a spline")
     SplineVariable("x", SplineGetter(np.linspace(0, 1, 4)), priors=[g, ok])  # both prior kinds are legal
+
+
+def test_component_attaches_to_a_pyarrow_table():
+    """Arrow ingest (SURVEY.md 8f rank 2): a pyarrow.Table stands in for the pandas frame;
+    a single-chunk null-free float64 column is handed on as a view of the Arrow buffer."""
+    pa = pytest.importorskip("pyarrow")
+    from anml_b200.data.component import Component
+    from anml_b200.data.frame import ArrowFrame, as_frame
+    from anml_b200.data.validator import NoNans
+
+    a = np.arange(5, dtype=np.float64)
+    table = pa.table({"a": a, "b": pa.array([1.0, None, 3.0, 4.0, 5.0]), "c": pa.chunked_array([[1.0, 2.0], [3.0, 4.0, 5.0]])})
+    frame = as_frame(table)
+    assert isinstance(frame, ArrowFrame) and as_frame(frame) is frame and len(frame) == 5
+    comp = Component("a", validators=[NoNans()])
+    comp.attach(frame)
+    np.testing.assert_array_equal(comp.value, a)
+    assert np.shares_memory(comp.value, table.column("a").chunk(0).to_numpy(zero_copy_only=True))
+    with pytest.raises(ValueError):
+        Component("b", validators=[NoNans()]).attach(frame)  # the null arrives as NaN
+    multi = Component("c")
+    multi.attach(table)  # a raw table is wrapped on the fly
+    np.testing.assert_array_equal(multi.value, [1.0, 2.0, 3.0, 4.0, 5.0])
+    icpt = Component("intercept", default_value=1.0)
+    icpt.attach(frame)
+    np.testing.assert_array_equal(icpt.value, np.ones(5))
+    assert "intercept" in frame and "intercept" not in table.column_names
+    with pytest.raises(KeyError):
+        Component("missing").attach(frame)
