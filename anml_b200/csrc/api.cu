@@ -71,6 +71,9 @@ struct anml_design {
     CUtensorMap tmap32;  // box 32 rows x 16 cols, 128B swizzle
     CUtensorMap tmap3d;  // (16 cols, rows, 16-column groups), box 16 x 32 x p/16: one TMA per 32-row block (p % 16 == 0 only)
     bool has3d = false;
+    CUtensorMap tmap64;    // box 64 rows x 16 cols: 64-row blocks of narrow designs (p <= 32)
+    CUtensorMap tmap3d64;  // box 16 x 64 x p/16
+    bool has64 = false, has3d64 = false;
     int sm_count = 0;
 };
 
@@ -229,6 +232,24 @@ static int encode_design_tmap(anml_design* d) {
         r = fn(&d->tmap3d, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, d->X, gdim3, gstride3, box3, estride3, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         d->has3d = (r == CUDA_SUCCESS);
+    }
+    memset(&d->tmap64, 0, sizeof(d->tmap64));
+    memset(&d->tmap3d64, 0, sizeof(d->tmap3d64));
+    d->has64 = d->has3d64 = false;
+    if (d->p <= 32) {
+        cuuint32_t box64[2] = {16, 64};
+        r = fn(&d->tmap64, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d->X, gdim, gstride, box64, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        d->has64 = (r == CUDA_SUCCESS);
+        if (d->has64 && d->p % 16 == 0) {
+            cuuint64_t gdim3[3] = {16, (cuuint64_t)d->n, (cuuint64_t)(d->p / 16)};
+            cuuint64_t gstride3[2] = {(cuuint64_t)d->ld * sizeof(double), 128};
+            cuuint32_t box3[3] = {16, 64, (cuuint32_t)(d->p / 16)};
+            cuuint32_t estride3[3] = {1, 1, 1};
+            r = fn(&d->tmap3d64, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, d->X, gdim3, gstride3, box3, estride3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            d->has3d64 = (r == CUDA_SUCCESS);
+        }
     }
     return ANML_OK;
 }
@@ -957,25 +978,32 @@ static int launch_fused_t(const anml_design* d, const FusedArgs& a, int grid, cu
     return ANML_OK;
 }
 
-template <int NB16, int NHELP, bool SIGNED, int MODE, bool TMA3D>
+template <int NB16, int NHELP, bool SIGNED, int MODE, bool TMA3D, int ROWS>
 static int launch_hess_tt(const anml_design* d, const FusedArgs& a, int grid, cudaStream_t st) {
-    using C = HessCfg<NB16, NHELP>;
+    using C = HessCfg<NB16, NHELP, ROWS>;
     static bool configured = false;
-    auto kern = fused_hess_kernel<NB16, NHELP, SIGNED, MODE, TMA3D>;
+    auto kern = fused_hess_kernel<NB16, NHELP, SIGNED, MODE, TMA3D, ROWS>;
     if (!configured) {
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured = true;
     }
-    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(TMA3D ? d->tmap3d : d->tmap32, a);
+    const CUtensorMap& tm = ROWS == 64 ? (TMA3D ? d->tmap3d64 : d->tmap64) : (TMA3D ? d->tmap3d : d->tmap32);
+    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tm, a);
     CU_TRY(cudaGetLastError());
     return ANML_OK;
 }
 
 template <int NB16, int NHELP, bool SIGNED, int MODE>
 static int launch_hess_t(const anml_design* d, const FusedArgs& a, int grid, cudaStream_t st) {
-    // one 3-D TMA per block when the width is a multiple of 16 (no partial column group)
-    if (d->has3d && d->p == 16 * NB16) return launch_hess_tt<NB16, NHELP, SIGNED, MODE, true>(d, a, grid, st);
-    return launch_hess_tt<NB16, NHELP, SIGNED, MODE, false>(d, a, grid, st);
+    // narrow designs (p <= 32) run 64-row blocks; one 3-D TMA per block when the width is a
+    // multiple of 16 (no partial column group)
+    if (NB16 <= 2 && d->has64) {
+        constexpr int R = NB16 <= 2 ? 64 : 32;  // (keeps the 64-row variants of the wide kernels uninstantiated)
+        if (d->has3d64 && d->p == 16 * NB16) return launch_hess_tt<NB16, NHELP, SIGNED, MODE, true, R>(d, a, grid, st);
+        return launch_hess_tt<NB16, NHELP, SIGNED, MODE, false, R>(d, a, grid, st);
+    }
+    if (d->has3d && d->p == 16 * NB16) return launch_hess_tt<NB16, NHELP, SIGNED, MODE, true, 32>(d, a, grid, st);
+    return launch_hess_tt<NB16, NHELP, SIGNED, MODE, false, 32>(d, a, grid, st);
 }
 
 // canonical link/family pairs have Hessian weights w > 0 (no sign handling in the tensor warp)

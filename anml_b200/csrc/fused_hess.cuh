@@ -41,7 +41,10 @@
 
 namespace anml {
 
-template <int NB16, int NHELP = 2>
+// ROWS = rows per block: 32, or 64 for narrow designs (p <= 32), where the per-block overhead of the
+// tensor warp (TMA re-arm, flag hand-off: ~700 cycles) would otherwise rival its DMMA time
+// (10 tiles x 8 k-steps x 16 cycles = 1280 at p = 32).  A 64-row block is two 32-row halves for the helpers.
+template <int NB16, int NHELP = 2, int ROWS = 32>
 struct HessCfg {
     static constexpr int TEAMS = 4;
     static constexpr int HELPERS = NHELP;  // per team
@@ -51,11 +54,14 @@ struct HessCfg {
     static constexpr int REGS_M = 216, REGS_H = 144;
     static constexpr int NB8 = 2 * NB16;
     static constexpr int NT = NB8 * (NB8 + 1) / 2;
-    static constexpr int BUF_BYTES = NB16 * 4096;  // NB16 boxes of 32 rows x 128 B
+    static constexpr int HALVES = ROWS / 32;
+    static constexpr int KSTEPS = ROWS / 4;
+    static constexpr int GROUP_BYTES = ROWS * 128;             // one 16-column group of the block
+    static constexpr int BUF_BYTES = NB16 * GROUP_BYTES;       // NB16 boxes of ROWS rows x 128 B
     static constexpr int NBUF = (49152 / BUF_BYTES) > 8 ? 8 : (49152 / BUF_BYTES);
     static constexpr int TEAM_BYTES = NBUF * BUF_BYTES;
     static constexpr int EL = (2 * NT + NB8 + 1) * 32;
-    static constexpr int SMEM_BYTES = 1024 + TEAMS * TEAM_BYTES + TEAMS * NBUF * 32 * 4 /*sign masks*/ + TEAMS * NBUF * 2 * 8 /*full barriers, ready flags*/ +
+    static constexpr int SMEM_BYTES = 1024 + TEAMS * TEAM_BYTES + TEAMS * NBUF * ROWS * 4 /*sign masks*/ + TEAMS * NBUF * 2 * 8 /*full barriers, ready flags*/ +
                                       16 * NB16 * 8 /*beta*/ + TEAMS * HELPERS * (NB8 + 1) * 32 * 8 /*helper g, obj; transpose scratch*/ +
                                       TEAMS * HELPERS * 64 * 8 /*helper r, sqrt|w|*/;
 };
@@ -83,7 +89,7 @@ __device__ __forceinline__ double flip_sign(double v, uint32_t mask) {  // mask 
 }
 
 // fragments of one 4-row k-step of the rescaled block: av[jb] = X~[row(t)][col(jb, g)]
-template <int NB16>
+template <int NB16, int GROUP_BYTES = 4096>
 __device__ __forceinline__ void load_kstep(double* av, uint32_t bp, int s, int g, int t) {
     // k-step s holds rows 16*(s>>2) + 8*((s>>1)&1) + (s&1) + 2t, t = 0..3
     const int xr = 2 * t + (s & 1);
@@ -91,7 +97,7 @@ __device__ __forceinline__ void load_kstep(double* av, uint32_t bp, int s, int g
     const uint32_t rp = bp + row * 128 + ((g ^ xr) << 4);
 #pragma unroll
     for (int j = 0; j < NB16; ++j) {
-        const double2 v = lds128(rp + j * 4096);
+        const double2 v = lds128(rp + j * GROUP_BYTES);
         av[2 * j] = v.x;
         av[2 * j + 1] = v.y;
     }
@@ -117,9 +123,10 @@ __device__ __forceinline__ void mma_kstep(double* acc, const double* av, uint32_
 // MODE 1: (r, w) read from a.rvec / a.wvec (blocks of the general path).
 // TMA3D: the tensor map is the 3-D view (16 cols, rows, column groups) and one instruction
 // fetches the whole block (api.cu encodes it when p is a multiple of 16).
-template <int NB16, int NHELP, bool SIGNED, int MODE, bool TMA3D>
+template <int NB16, int NHELP, bool SIGNED, int MODE, bool TMA3D, int ROWS>
 __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const __grid_constant__ CUtensorMap tmap32, const FusedArgs a) {
-    using C = HessCfg<NB16, NHELP>;
+    using C = HessCfg<NB16, NHELP, ROWS>;
+    constexpr int KSTEPS = C::KSTEPS, GB = C::GROUP_BYTES, SIGN_BYTES = ROWS * 4;
     constexpr int NB8 = C::NB8, NT = C::NT, NBUF = C::NBUF, TEAMS = C::TEAMS;
 
     extern __shared__ unsigned char smem_raw[];
@@ -127,7 +134,7 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
     unsigned char* smem = smem_raw + (smem_base - smem_u32(smem_raw));
     // layout: rings | sign masks | barriers | beta | helper records (gradient rows, objective row)
     const uint32_t signs_base = smem_base + TEAMS * C::TEAM_BYTES;
-    const uint32_t bars_base = signs_base + TEAMS * NBUF * 32 * 4;
+    const uint32_t bars_base = signs_base + TEAMS * NBUF * SIGN_BYTES;
     const uint32_t beta_base = bars_base + TEAMS * NBUF * 2 * 8;
     const uint32_t hrec_base = beta_base + 16 * NB16 * 8;
     const uint32_t hterm_base = hrec_base + TEAMS * C::HELPERS * (NB8 + 1) * 256;
@@ -150,11 +157,11 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
     __syncthreads();
 
     const uint32_t ring_u32 = smem_base + team * C::TEAM_BYTES;
-    const uint32_t sign_u32 = signs_base + team * NBUF * 32 * 4;        // [buf][32] sign bit of w per row
+    const uint32_t sign_u32 = signs_base + team * NBUF * SIGN_BYTES;    // [buf][ROWS] sign bit of w per row
     const uint32_t full_u32 = bars_base + team * NBUF * 2 * 8;          // full[b]  : TMA bytes landed
     const uint32_t rdy_u32 = full_u32 + NBUF * 8;                       // ready[b] : u32 sequence flag, block rescaled + signs published
 
-    const long long nblk = (a.n + 31) >> 5;
+    const long long nblk = (a.n + ROWS - 1) / ROWS;
     const long long gp = (long long)blockIdx.x * TEAMS + team;
     const long long GP = (long long)gridDim.x * TEAMS;
     const long long nmine = (nblk > gp) ? (nblk - gp + GP - 1) / GP : 0;
@@ -166,7 +173,7 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
         // ============================ tensor warp ============================
         if (NHELP == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::REGS_M));
         auto issue = [&](long long blk_seq, int buf) {
-            const long long row0 = (gp + blk_seq * GP) * 32;
+            const long long row0 = (gp + blk_seq * GP) * ROWS;
             const uint32_t bar = full_u32 + buf * 8;
             const uint32_t dst = ring_u32 + buf * C::BUF_BYTES;
             mbar_arrive_expect_tx(bar, C::BUF_BYTES);
@@ -174,7 +181,7 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
                 tma_load_3d(dst, &tmap32, 0, (int)row0, 0, bar);
             } else {
 #pragma unroll
-                for (int j = 0; j < NB16; ++j) tma_load_2d(dst + j * 4096, &tmap32, 16 * j, (int)row0, bar);
+                for (int j = 0; j < NB16; ++j) tma_load_2d(dst + j * GB, &tmap32, 16 * j, (int)row0, bar);
             }
         };
         if (lane == 0) {
@@ -199,27 +206,27 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
             uint32_t f0;
             do { f0 = lds32_sync(rdy_u32); } while (f0 != 1u);
             // (f0 ^ 1) == 0: an address dependency, so no fragment load can be issued before the flag arrived
-            load_kstep<NB16>(avA, ring_u32 + (f0 ^ 1u), 0, g, t);
+            load_kstep<NB16, GB>(avA, ring_u32 + (f0 ^ 1u), 0, g, t);
             if (SIGNED) sgA = lds32(sign_u32 + (f0 ^ 1u) + t * 4);
         }
         for (long long i = 0; i < nmine; ++i) {
             phase_bits ^= 1u << buf;
             const uint32_t bp = ring_u32 + buf * C::BUF_BYTES;
-            const uint32_t sb = sign_u32 + buf * 128;
+            const uint32_t sb = sign_u32 + buf * SIGN_BYTES;
             const int nbuf = (buf + 1 == NBUF) ? 0 : buf + 1;
             const bool has_next = i + 1 < nmine;
             const uint32_t want_flag = (uint32_t)(i + 2);  // block i+1 published
             uint32_t seen_flag = 0;
 #pragma unroll
-            for (int s = 0; s < 8; s += 2) {
+            for (int s = 0; s < KSTEPS; s += 2) {
                 // even k-step on set A, prefetch k-step s+1 into set B
-                load_kstep<NB16>(avB, bp, s + 1, g, t);
+                load_kstep<NB16, GB>(avB, bp, s + 1, g, t);
                 if (SIGNED) sgB = lds32(sb + (4 * (s + 1) + t) * 4);
                 mma_kstep<NB8, SIGNED>(acc, avA, sgA);
-                if (s == 4) seen_flag = lds32_sync(rdy_u32 + nbuf * 8);  // consumed two k-steps later
+                if (s == KSTEPS - 4) seen_flag = lds32_sync(rdy_u32 + nbuf * 8);  // consumed two k-steps later
                 // odd k-step on set B, prefetch k-step s+2 (or the next block's first) into set A
-                if (s + 2 < 8) {
-                    load_kstep<NB16>(avA, bp, s + 2, g, t);
+                if (s + 2 < KSTEPS) {
+                    load_kstep<NB16, GB>(avA, bp, s + 2, g, t);
                     if (SIGNED) sgA = lds32(sb + (4 * (s + 2) + t) * 4);
                 } else {
                     // this block now lives entirely in registers: hand its buffer back to TMA
@@ -236,8 +243,8 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
                     // (seen ^ want) == 0: address dependency on the flag (see prologue).  Without a next
                     // block this reads stale but valid shared memory; the values are never used.
                     const uint32_t dep = seen_flag ^ want_flag;
-                    load_kstep<NB16>(avA, ring_u32 + nbuf * C::BUF_BYTES + dep, 0, g, t);
-                    if (SIGNED) sgA = lds32(sign_u32 + nbuf * 128 + dep + t * 4);
+                    load_kstep<NB16, GB>(avA, ring_u32 + nbuf * C::BUF_BYTES + dep, 0, g, t);
+                    if (SIGNED) sgA = lds32(sign_u32 + nbuf * SIGN_BYTES + dep + t * 4);
                 }
                 mma_kstep<NB8, SIGNED>(acc, avB, sgB);
             }
@@ -273,10 +280,12 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
             mbar_wait(full_u32 + buf * 8, (phase_bits >> buf) & 1u);
             phase_bits ^= 1u << buf;
             if ((int)(i % C::HELPERS) != hid) continue;
-            const long long row = (gp + i * GP) * 32 + R;
+#pragma unroll 1
+            for (int hh = 0; hh < C::HALVES; ++hh) {  // a 64-row block is handled as two 32-row halves
+            const long long row = (gp + i * GP) * ROWS + 32 * hh + R;
             const bool valid = row < a.n;
             double rr = 0.0, ww = 0.0, sc = 0.0;
-            const uint32_t bp = ring_u32 + buf * C::BUF_BYTES;
+            const uint32_t bp = ring_u32 + buf * C::BUF_BYTES + hh * 4096;
             if (MODE == 0) {
                 // per-row global loads first: their latency hides behind the dot products
                 double off = 0.0, ob = 0.0, se = 1.0;
@@ -295,7 +304,7 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
                     double d = 0.0;
 #pragma unroll
                     for (int j = 0; j < NB16; ++j) {
-                        const double2 v = lds128(rp + j * 4096);
+                        const double2 v = lds128(rp + j * GB);
                         d = fma(v.x, bsl[j].x, d);
                         d = fma(v.y, bsl[j].y, d);
                     }
@@ -344,7 +353,7 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
                 ww = a.wvec[row];
                 sc = sqrt(fabs(ww));
             }
-            if (SIGNED) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sign_u32 + buf * 128 + lane * 4), "r"(ww < 0.0 ? 0x80000000u : 0u) : "memory");
+            if (SIGNED) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sign_u32 + buf * SIGN_BYTES + (32 * hh + lane) * 4), "r"(ww < 0.0 ? 0x80000000u : 0u) : "memory");
             // ---- pass 2: gradient, and rescale the block in place to sqrt(|w|) x
             // (r, sqrt|w|) of the 32 rows go through shared memory: 2 stores + broadcast loads
             // instead of 32 shuffles
@@ -360,13 +369,14 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
                 const double sv = lds64(ht_u32 + 256 + (4 * s + t) * 8);
 #pragma unroll
                 for (int j = 0; j < NB16; ++j) {
-                    const double2 v = lds128(rp + j * 4096);
+                    const double2 v = lds128(rp + j * GB);
                     gacc[2 * j] = fma(rv, v.x, gacc[2 * j]);
                     gacc[2 * j + 1] = fma(rv, v.y, gacc[2 * j + 1]);
-                    sts128(rp + j * 4096, sv * v.x, sv * v.y);
+                    sts128(rp + j * GB, sv * v.x, sv * v.y);
                 }
             }
             __syncwarp();
+            }  // halves
             if (lane == 0) {
                 __threadfence_block();  // the block's stores before the flag
                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(rdy_u32 + buf * 8), "r"((uint32_t)(i + 1)) : "memory");
