@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -964,14 +965,23 @@ static EventPair* next_events(anml_model* m) {
     return &m->ev_pool[m->ev_used++];
 }
 
+// cudaFuncSetAttribute is per device: remember which devices a kernel has been configured on
+struct ConfiguredOn {
+    std::atomic<unsigned long long> mask{0};
+    bool has(int device) const { return device >= 0 && device < 64 && ((mask.load(std::memory_order_acquire) >> device) & 1ull); }
+    void set(int device) {
+        if (device >= 0 && device < 64) mask.fetch_or(1ull << device, std::memory_order_release);
+    }
+};
+
 template <int NB16, bool HESS, int MODE>
 static int launch_fused_t(const anml_design* d, const FusedArgs& a, int grid, cudaStream_t st) {
     using C = FusedCfg<NB16>;
-    static bool configured = false;
+    static ConfiguredOn configured;
     auto kern = fused_eval_kernel<NB16, HESS, MODE>;
-    if (!configured) {
+    if (!configured.has(d->device)) {
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        configured = true;
+        configured.set(d->device);
     }
     kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(d->tmap, a);
     CU_TRY(cudaGetLastError());
@@ -981,11 +991,11 @@ static int launch_fused_t(const anml_design* d, const FusedArgs& a, int grid, cu
 template <int NB16, int NHELP, bool SIGNED, int MODE, bool TMA3D, int ROWS>
 static int launch_hess_tt(const anml_design* d, const FusedArgs& a, int grid, cudaStream_t st) {
     using C = HessCfg<NB16, NHELP, ROWS>;
-    static bool configured = false;
+    static ConfiguredOn configured;
     auto kern = fused_hess_kernel<NB16, NHELP, SIGNED, MODE, TMA3D, ROWS>;
-    if (!configured) {
+    if (!configured.has(d->device)) {
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        configured = true;
+        configured.set(d->device);
     }
     const CUtensorMap& tm = ROWS == 64 ? (TMA3D ? d->tmap3d64 : d->tmap64) : (TMA3D ? d->tmap3d : d->tmap32);
     kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tm, a);
@@ -1160,10 +1170,10 @@ static int run_wide_hessian(anml_model* m, const anml_design* da, const anml_des
         CU_TRY(cudaMalloc(&m->d_wide, (size_t)need * sizeof(double)));
         m->wide_len = need;
     }
-    static bool configured = false;
-    if (!configured) {
+    static ConfiguredOn configured;
+    if (!configured.has(m->device)) {
         CU_TRY(cudaFuncSetAttribute(wide_hessian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WIDE_SMEM_BYTES));
-        configured = true;
+        configured.set(m->device);
     }
     WideArgs a;
     a.n_pad = m->n_pad; a.chunk_rows = chunk_rows; a.npairs = npairs; a.nbj = nbb; a.symmetric = symmetric ? 1 : 0;
