@@ -134,3 +134,143 @@ def test_config3_spline_50m_rows_partition_of_unity_and_indices():
     assert np.all(H0[np.abs(i - j) > deg] == 0.0) and np.all(np.diag(H0) > 0)
     assert abs(H0.sum() - n) <= 1e-10 * n  # sum_ij H_ij = sum_rows (sum_j B_j)^2 = n
     assert abs(o0 - 0.5 * float((obs**2).sum())) <= 1e-12 * o0
+
+
+def _free(torch):
+    import gc
+
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+def test_north_star_logistic_100m_rows_against_torch_fp64():
+    """BASELINE north star: binomial/expit, 1e8 rows x 64 on one GPU (51.2 GB resident)."""
+    torch = _torch()
+    if torch.cuda.get_device_properties(0).total_memory < 120e9:
+        pytest.skip("needs a 180 GB device")
+    n, p = 100_000_000, 64
+    X, obs, beta_true = make_logistic(torch, n, p, SEED)
+    x = (0.5 * beta_true).cpu().numpy()
+    model = native_model(X, obs, 0, n)
+    o, g, H = model.eval(x)
+    assert np.array_equal(H, H.T)
+    xb = torch.from_numpy(x).cuda()
+    obj = torch.zeros((), dtype=torch.float64, device="cuda")
+    grad = torch.zeros(p, dtype=torch.float64, device="cuda")
+    hess = torch.zeros((p, p), dtype=torch.float64, device="cuda")
+    chunk = 1 << 21
+    for lo in range(0, n, chunk):
+        Xc, oc = X[lo:lo + chunk], obs[lo:lo + chunk]
+        y = Xc @ xb
+        th = torch.sigmoid(y)
+        obj += (torch.nn.functional.softplus(-y) + (1 - oc) * y).sum()
+        grad += Xc.t() @ (th - oc)
+        hess += (Xc.t() * (th * (1 - th))) @ Xc
+    obj += 0.5 * (xb**2).sum()
+    grad += xb
+    hess += torch.eye(p, dtype=torch.float64, device="cuda")
+    ow, gw, Hw = float(obj), grad.cpu().numpy(), hess.cpu().numpy()
+    assert abs(o - ow) <= 1e-10 * abs(ow)
+    assert np.abs(g - gw).max() <= 1e-10 * np.abs(gw).max()
+    assert np.abs(H - Hw).max() <= 1e-9 * np.abs(Hw).max()
+    del model, X, obs
+    _free(torch)
+
+
+def test_config4_two_parameter_shared_design_25m_rows_against_torch_fp64():
+    """BASELINE config #4 (mean identity + variance exp over the same 64 columns) at the
+    2.5e7-row shard of a 4-GPU run: l = 1/2 log v + 1/2 (obs - mu)^2 / v, v = exp(X b_s)."""
+    torch = _torch()
+    from anml_b200 import _native as N
+
+    n, p = 25_000_000, 64
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev)
+    g.manual_seed(SEED + 4)
+    bm = torch.randn(p, dtype=torch.float64, device=dev, generator=g) * 0.1
+    bs = torch.randn(p, dtype=torch.float64, device=dev, generator=g) * 0.05
+    X = torch.empty((n, p), dtype=torch.float64, device=dev)
+    obs = torch.empty(n, dtype=torch.float64, device=dev)
+    chunk = 1 << 21
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        X[lo:hi].normal_(generator=g)
+        X[lo:hi, 0] = 1.0
+        obs[lo:hi] = X[lo:hi] @ bm + torch.exp(0.5 * (X[lo:hi] @ bs)) * torch.randn(hi - lo, dtype=torch.float64, device=dev, generator=g)
+    d = N.Design.wrap(X.data_ptr(), n, p, p, keepalive=X)
+    m = N.NativeModel(n, "gaussian_meanvar", 2)
+    m.set_param(0, d, N.LINK_CODES["Identity"])
+    m.set_param(1, d, N.LINK_CODES["Exp"])
+    m.set_obs(dev_ptr=obs.data_ptr(), keepalive=obs)
+    xm, xs = 0.5 * bm, 0.5 * bs
+    x = torch.cat([xm, xs]).cpu().numpy()
+    o, gr, H = m.eval(x)
+    assert H.shape == (2 * p, 2 * p) and np.array_equal(H, H.T)
+    obj = torch.zeros((), dtype=torch.float64, device=dev)
+    grad = torch.zeros(2 * p, dtype=torch.float64, device=dev)
+    hess = torch.zeros((2 * p, 2 * p), dtype=torch.float64, device=dev)
+    for lo in range(0, n, chunk):
+        Xc, oc = X[lo:lo + chunk], obs[lo:lo + chunk]
+        mu, ls = Xc @ xm, Xc @ xs
+        iv = torch.exp(-ls)
+        res = oc - mu
+        obj += (0.5 * ls + 0.5 * res * res * iv).sum()
+        r0 = -res * iv                       # dl/dmu
+        r1 = 0.5 - 0.5 * res * res * iv      # dl/dlog v
+        w00, w01, w11 = iv, res * iv, 0.5 * res * res * iv
+        grad[:p] += Xc.t() @ r0
+        grad[p:] += Xc.t() @ r1
+        hess[:p, :p] += (Xc.t() * w00) @ Xc
+        hess[:p, p:] += (Xc.t() * w01) @ Xc
+        hess[p:, p:] += (Xc.t() * w11) @ Xc
+    hess[p:, :p] = hess[:p, p:].t()
+    ow, gw, Hw = float(obj), grad.cpu().numpy(), hess.cpu().numpy()
+    assert abs(o - ow) <= 1e-10 * abs(ow)
+    assert np.abs(gr - gw).max() <= 1e-10 * np.abs(gw).max()
+    assert np.abs(H - Hw).max() <= 1e-9 * np.abs(Hw).max()
+    del m, d, X, obs
+    _free(torch)
+
+
+def test_config5_wide_design_shard_against_torch_fp64():
+    """BASELINE config #5 at the per-GPU shard of the 8-GPU run: 2.5e6 rows x 1024 columns
+    (20.5 GB), binomial/expit, Hessian on the wide DMMA kernel."""
+    torch = _torch()
+    from anml_b200 import _native as N
+
+    n, p = 2_500_000, 1024
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev)
+    g.manual_seed(SEED + 5)
+    beta_true = torch.randn(p, dtype=torch.float64, device=dev, generator=g) * 0.025
+    X = torch.empty((n, p), dtype=torch.float64, device=dev)
+    obs = torch.empty(n, dtype=torch.float64, device=dev)
+    chunk = 1 << 17
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        X[lo:hi].normal_(generator=g)
+        X[lo:hi, 0] = 1.0
+        obs[lo:hi] = (torch.rand(hi - lo, dtype=torch.float64, device=dev, generator=g) < torch.sigmoid(X[lo:hi] @ beta_true)).double()
+    d = N.Design.wrap(X.data_ptr(), n, p, p, keepalive=X)
+    m = N.NativeModel(n, "binomial", 1)
+    m.set_param(0, d, N.LINK_CODES["Expit"])
+    m.set_obs(dev_ptr=obs.data_ptr(), keepalive=obs)
+    xb = 0.5 * beta_true
+    o, gr, H = m.eval(xb.cpu().numpy())
+    assert np.array_equal(H, H.T)
+    obj = torch.zeros((), dtype=torch.float64, device=dev)
+    grad = torch.zeros(p, dtype=torch.float64, device=dev)
+    hess = torch.zeros((p, p), dtype=torch.float64, device=dev)
+    for lo in range(0, n, chunk):
+        Xc, oc = X[lo:lo + chunk], obs[lo:lo + chunk]
+        y = Xc @ xb
+        th = torch.sigmoid(y)
+        obj += (torch.nn.functional.softplus(-y) + (1 - oc) * y).sum()
+        grad += Xc.t() @ (th - oc)
+        hess += (Xc.t() * (th * (1 - th))) @ Xc
+    ow, gw, Hw = float(obj), grad.cpu().numpy(), hess.cpu().numpy()
+    assert abs(o - ow) <= 1e-10 * abs(ow)
+    assert np.abs(gr - gw).max() <= 1e-10 * np.abs(gw).max()
+    assert np.abs(H - Hw).max() <= 1e-9 * np.abs(Hw).max()
+    del m, d, X, obs
+    _free(torch)
