@@ -11,25 +11,31 @@
 //
 // Structure: one persistent CTA of 12 warps per SM = 4 teams (one per scheduler):
 // tensor warp M (warp q) + helper warps H0, H1 (warps q+4, q+8); setmaxnreg moves
-// registers from helpers to M.  Each team owns 32-row blocks b = gp, gp+GP, ... and a
-// private ring of NBUF block buffers (32 rows x 16*NB16 columns, TMA boxes of 32x16
-// doubles, 128-byte swizzle, zero fill outside the matrix).
+// registers from helpers to M.  Each team owns row blocks b = gp, gp+GP, ... (32 rows,
+// 64 for designs of at most 32 columns) and a private ring of NBUF block buffers
+// ([column group][row][16 doubles], 128-byte swizzle, zero fill outside the matrix),
+// filled by one 3-D TMA per block when p is a multiple of 16, else by one 2-D box per
+// 16-column group.
 //   * helper H(i&1), block i: waits for the TMA bytes; pass 1: y = X beta on
-//     MMA-layout fragments + 8-lane transposing reduction, then link + family terms,
-//     one row per lane; pass 2 over the same block: g += r_k x_k and the block is
-//     rescaled IN PLACE to sqrt(|w_k|) x_k; publishes sign(w) and arrives on terms[b].
+//     MMA-layout fragments, partial sums transposed through shared memory, then link +
+//     family terms, one row per lane (the logistic log(1 + e^-y) is not taken per row:
+//     rowmath.cuh LogProduct); pass 2 over the same block: g += r_k x_k and the block is
+//     rescaled IN PLACE to sqrt(|w_k|) x_k; publishes sign(w) and then the sequence
+//     flag ready[b] = i + 1.
 //   * tensor warp M: X~ = sqrt(|w|) X makes H = X~^T X~, so A and B fragments are the
 //     same registers: per 4-row k-step 4 LDS.128 and 36 DMMAs (tiles on/below the
 //     diagonal at p = 64), software-pipelined over two fragment sets.  (Non-canonical
 //     link/family pairs can have w < 0: then B = -A for that row, an integer XOR on
-//     the sign bit -- still no FP64-pipe instruction.)  When a block is entirely in
-//     registers M re-arms TMA for its buffer.
+//     the sign bit -- still no FP64-pipe instruction.)  It reads ready[b] of the next
+//     block with a plain LDS two k-steps early (an mbarrier wait there cost 3 %), and
+//     when a block is entirely in registers it re-arms TMA for its buffer.
 //
-// Ordering: M finishes block i only after the helper arrived on terms[b] for it,
-// which is after the helper's last access to the buffer; so when M re-issues TMA
-// nobody touches the buffer (fence.proxy.async orders the helper's generic-proxy
-// stores before the async-proxy refill).  Helpers observe every phase of every
-// full[] barrier, also for blocks of the other helper (a parity wait cannot tell
+// Ordering: M starts block i only after the helper published ready[b] for it, which
+// is after the helper's last access to the buffer (threadfence_block before the flag;
+// M's first fragment address carries a dependency on the flag value); so when M
+// re-issues TMA nobody touches the buffer (fence.proxy.async orders the helper's
+// generic-proxy stores before the async-proxy refill).  Helpers observe every phase of
+// every full[] barrier, also for blocks of the other helper (a parity wait cannot tell
 // phases two apart).
 //
 // Partial-record layout is the one of fused_eval_kernel (reduce_partials_kernel
