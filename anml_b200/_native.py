@@ -55,6 +55,7 @@ SIGNATURES = {
     "anml_model_set_obs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "anml_model_set_obs_se": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "anml_model_set_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "anml_model_enable_banded_spline": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _c_double_p, C.c_int, C.c_int]),
     "anml_model_set_gaussian_prior": (C.c_int, [C.c_void_p, C.c_int, _c_double_p, _c_double_p, C.c_int, _c_double_p, _c_double_p, _c_double_p]),
     "anml_model_set_prior_enabled": (C.c_int, [C.c_void_p, C.c_int]),
     "anml_model_num_coefs": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
@@ -402,6 +403,24 @@ class NativeModel:
             lin_mat, lin_mean, lin_sd = as_f64(lin_mat), as_f64(lin_mean), as_f64(lin_sd)
             check(load().anml_model_set_gaussian_prior(self.handle, k, dptr(mean), dptr(sd), lin_mat.shape[0],
                                                        dptr(lin_mat), dptr(lin_mean), dptr(lin_sd)))
+
+    def enable_banded_spline(self, knots, degree: int, x=None, x_dev_ptr=None) -> bool:
+        """Evaluate a one-spline model from the abscissae instead of the dense design
+        (csrc/spline_eval.cuh).  Returns False -- and leaves the dense path in place --
+        when the library declines (abscissae outside the knot span, degree > 3)."""
+        knots = as_f64(knots, "knots")
+        if x_dev_ptr is not None:
+            xp, on_dev, keep = _as_ptr(x_dev_ptr), 1, None
+        else:
+            keep = as_f64(np.asarray(x).ravel(), "x")
+            if keep.size != self.n_rows:
+                raise ValueError("spline abscissae length does not match the model")
+            xp, on_dev = keep.ctypes.data_as(C.c_void_p), 0
+        status = load().anml_model_enable_banded_spline(self.handle, xp, on_dev, dptr(knots), knots.size, int(degree))
+        if status == 5:  # ANML_EUNSUPPORTED
+            return False
+        check(status)
+        return True
 
     def set_prior_enabled(self, enabled: bool):
         check(load().anml_model_set_prior_enabled(self.handle, 1 if enabled else 0))

@@ -19,6 +19,7 @@
 #include "fused_hess.cuh"
 #include "generic.cuh"
 #include "spline.cuh"
+#include "spline_eval.cuh"
 #include "upload.cuh"
 #include "wide_hessian.cuh"
 
@@ -128,6 +129,15 @@ struct anml_model {
     double* vec[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // y0 y1 r0 r1 w00 w01 w11
     double* d_wide = nullptr;
     long long wide_len = 0;
+    // banded spline evaluator (spline_eval.cuh): rows sorted by x, per-row vectors gathered into that order
+    struct Banded {
+        bool enabled = false, gathered = false;
+        int nk = 0, degree = 0, nb = 0, rec = 0;
+        long long nwarps = 0, rows_per_warp = 0;
+        double *xs = nullptr, *t_dev = nullptr, *coef = nullptr, *partials = nullptr, *reduced = nullptr;
+        int32_t* perm = nullptr;
+        double *obs_s = nullptr, *se_s = nullptr, *off_s = nullptr, *w_s = nullptr;
+    } banded;
     // timing of the dominant kernel
     std::vector<EventPair> ev_pool;
     size_t ev_used = 0;
@@ -754,11 +764,21 @@ static void free_eval_buffers(anml_model* m) {
     m->ready = false;
 }
 
+static void free_banded(anml_model* m) {
+    anml_model::Banded& b = m->banded;
+    double* bufs[] = {b.xs, b.t_dev, b.coef, b.partials, b.reduced, b.obs_s, b.se_s, b.off_s, b.w_s};
+    for (double* q : bufs)
+        if (q) cudaFree(q);
+    if (b.perm) cudaFree(b.perm);
+    b = anml_model::Banded();
+}
+
 extern "C" int anml_model_destroy(anml_model* m) {
     if (!m) return ANML_OK;
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     free_eval_buffers(m);
+    free_banded(m);
     for (int k = 0; k < 2; ++k) free_prior(m->par[k].prior);
     if (m->obs_owned) cudaFree(m->obs_owned);
     if (m->se_owned) cudaFree(m->se_owned);
@@ -788,12 +808,14 @@ extern "C" int anml_model_set_param(anml_model* m, int k, const anml_design* des
     m->par[k].design = design;
     m->par[k].link = link;
     m->par[k].offset = offset_dev;
+    free_banded(m);  // tied to the previous design; the caller enables it again after set_param
     return ANML_OK;
 }
 
 static int set_row_vector(anml_model* m, const double* src, int on_device, const double** view, double** owned) {
     CU_TRY(cudaSetDevice(m->device));
     if (m->stream) CU_TRY(cudaStreamSynchronize(m->stream));
+    m->banded.gathered = false;  // the sorted copies are stale
     if (*owned) {
         CU_TRY(cudaFree(*owned));
         *owned = nullptr;
@@ -1192,6 +1214,148 @@ static int run_wide_hessian(anml_model* m, const anml_design* da, const anml_des
     return ANML_OK;
 }
 
+// ----------------------------------------------------------------------------
+// banded spline evaluator (spline_eval.cuh)
+// ----------------------------------------------------------------------------
+constexpr int BANDED_CTAS_PER_SM = 2;  // 256-thread CTAs of 92 registers: two fit, and the row loop is latency-bound
+
+static int gather_sorted(anml_model* m, const double* src, double** dst, cudaStream_t st) {
+    if (!src) {
+        if (*dst) CU_TRY(cudaFree(*dst));
+        *dst = nullptr;
+        return ANML_OK;
+    }
+    if (!*dst) CU_TRY(cudaMalloc(dst, (size_t)m->n * sizeof(double)));
+    gather_rows_kernel<<<grid_for(m->n, 256, m->sm_count, 8), 256, 0, st>>>(*dst, src, m->banded.perm, m->n);
+    CU_TRY(cudaGetLastError());
+    return ANML_OK;
+}
+
+static int eval_banded(anml_model* m, int want, cudaStream_t st) {
+    anml_model::Banded& b = m->banded;
+    if (!m->obs) return fail(ANML_ESTATE, "observations not set");
+    if (!b.gathered) {
+        TRY(gather_sorted(m, m->obs, &b.obs_s, st));
+        TRY(gather_sorted(m, m->se, &b.se_s, st));
+        TRY(gather_sorted(m, m->par[0].offset, &b.off_s, st));
+        TRY(gather_sorted(m, m->weights, &b.w_s, st));
+        b.gathered = true;
+    }
+    const bool hess = (want & ANML_WANT_HESS) != 0;
+    BandedArgs a;
+    a.xs = b.xs; a.obs = b.obs_s; a.se = b.se_s; a.offset = b.off_s; a.weights = b.w_s;
+    a.n = m->n; a.t = b.t_dev; a.coef = b.coef; a.nk = b.nk; a.beta = m->d_beta;
+    const size_t coef_bytes = (size_t)(b.nk - 1) * (b.degree + 1) * (b.degree + 1) * sizeof(double);
+    a.coef_in_smem = coef_bytes <= 24 * 1024 ? 1 : 0;
+    a.family = m->family; a.link = m->par[0].link; a.fast = m->no_fast ? 0 : 1; a.want_hess = hess ? 1 : 0;
+    a.rows_per_warp = b.rows_per_warp; a.partials = b.partials; a.status = m->d_status;
+    CU_TRY(cudaMemsetAsync(b.partials, 0, (size_t)b.nwarps * b.rec * sizeof(double), st));
+    const int grid = (int)(b.nwarps / 8);
+    const size_t smem = (size_t)(((b.nk + 2 * b.degree + 1) & ~1) + ((b.nb + 1) & ~1)) * sizeof(double) + (a.coef_in_smem ? coef_bytes : 0);
+    EventPair* ep = next_events(m);
+    if (ep) CU_TRY(cudaEventRecord(ep->a, st));
+    switch (b.degree) {
+        case 1: spline_banded_eval_kernel<1><<<grid, 256, smem, st>>>(a); break;
+        case 2: spline_banded_eval_kernel<2><<<grid, 256, smem, st>>>(a); break;
+        default: spline_banded_eval_kernel<3><<<grid, 256, smem, st>>>(a); break;
+    }
+    CU_TRY(cudaGetLastError());
+    if (ep) CU_TRY(cudaEventRecord(ep->b, st));
+    banded_reduce_kernel<<<(b.rec + 31) / 32, dim3(32, 32), 0, st>>>(b.partials, b.nwarps, b.rec, b.reduced);
+    CU_TRY(cudaGetLastError());
+    banded_assemble_kernel<<<(1 + m->P + (hess ? m->P * m->P : 0) + 255) / 256, 256, 0, st>>>(b.reduced, b.nk - 1, b.degree, hess ? 1 : 0, m->d_packed, m->P);
+    CU_TRY(cudaGetLastError());
+    m->main_launches += 1;
+    m->all_launches += 3;
+    return ANML_OK;
+}
+
+extern "C" int anml_model_enable_banded_spline(anml_model* m, const double* x, int x_on_device, const double* knots, int n_knots, int degree) {
+    if (!m || !x || !knots) return fail(ANML_EINVAL, "anml_model_enable_banded_spline: NULL argument");
+    if (m->K != 1 || !m->par[0].design) return fail(ANML_ESTATE, "the banded spline evaluator needs a one-parameter model with its design set");
+    if (degree < 1 || degree > 3) return fail(ANML_EUNSUPPORTED, "banded spline evaluator: degree %d (supported: 1..3)", degree);
+    if (n_knots < 2 || n_knots > SPLINE_MAX_KNOTS) return fail(ANML_EINVAL, "spline needs between 2 and %d knots", SPLINE_MAX_KNOTS);
+    const int nb = n_knots - 1 + degree;
+    if (m->par[0].design->p != nb) return fail(ANML_EINVAL, "design has %d columns, the spline %d bases", m->par[0].design->p, nb);
+    if (m->n <= 0 || m->n > 2147483000LL) return fail(ANML_EUNSUPPORTED, "banded spline evaluator: unsupported row count");
+    for (int i = 1; i < n_knots; ++i)
+        if (!(knots[i] >= knots[i - 1])) return fail(ANML_EINVAL, "spline knots must be sorted ascending");
+    CU_TRY(cudaSetDevice(m->device));
+    if (m->stream) CU_TRY(cudaStreamSynchronize(m->stream));
+    free_banded(m);
+    anml_model::Banded& b = m->banded;
+    const long long n = m->n;
+    const double* xd = nullptr;
+    double* owned = nullptr;
+    TRY(vector_on_device(m->device, m->sm_count, x, n, x_on_device, &xd, &owned));
+    int32_t* iota = nullptr;
+    void* temp = nullptr;
+    size_t temp_bytes = 0;
+    cudaError_t e = cudaMalloc(&b.xs, (size_t)n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&b.perm, (size_t)n * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&iota, (size_t)n * sizeof(int32_t));
+    if (e == cudaSuccess) {
+        iota_kernel<<<grid_for(n, 256, m->sm_count, 8), 256>>>(iota, n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, xd, b.xs, iota, b.perm, (int)n);
+    if (e == cudaSuccess) e = cudaMalloc(&temp, temp_bytes ? temp_bytes : 16);
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, xd, b.xs, iota, b.perm, (int)n);
+    double ends[2] = {0.0, 0.0};
+    if (e == cudaSuccess) e = cudaMemcpy(&ends[0], b.xs, sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(&ends[1], b.xs + (n - 1), sizeof(double), cudaMemcpyDeviceToHost);
+    if (iota) cudaFree(iota);
+    if (temp) cudaFree(temp);
+    if (owned) cudaFree(owned);
+    if (e != cudaSuccess) {
+        const int code = (e == cudaErrorMemoryAllocation) ? ANML_ENOMEM : ANML_ECUDA;
+        (void)cudaGetLastError();
+        free_banded(m);
+        return fail(code, "anml_model_enable_banded_spline: %s", cudaGetErrorString(e));
+    }
+    // NaN sorts last, so both ends inside the knot span means every abscissa is (no extrapolation on this path)
+    if (!(ends[0] >= knots[0] && ends[1] <= knots[n_knots - 1])) {
+        free_banded(m);
+        return fail(ANML_EUNSUPPORTED, "banded spline evaluator: abscissae [%g, %g] leave the knot span [%g, %g]", ends[0], ends[1], knots[0],
+                    knots[n_knots - 1]);
+    }
+    const int nt = n_knots + 2 * degree;
+    std::vector<double> t(nt);
+    for (int i = 0; i < degree; ++i) t[i] = knots[0];
+    for (int i = 0; i < n_knots; ++i) t[degree + i] = knots[i];
+    for (int i = 0; i < degree; ++i) t[degree + n_knots + i] = knots[n_knots - 1];
+    const int slots = (degree + 1) + (degree + 1) * (degree + 2) / 2;
+    b.nk = n_knots; b.degree = degree; b.nb = nb; b.rec = (n_knots - 1) * slots + 1;
+    b.nwarps = (long long)m->sm_count * 8 * BANDED_CTAS_PER_SM;
+    long long rpw = (n + b.nwarps - 1) / b.nwarps;
+    b.rows_per_warp = (rpw + 31) / 32 * 32;
+    e = cudaMalloc(&b.t_dev, nt * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(b.t_dev, t.data(), nt * sizeof(double), cudaMemcpyHostToDevice);
+    const int ncoef = (n_knots - 1) * (degree + 1) * (degree + 1);
+    if (e == cudaSuccess) e = cudaMalloc(&b.coef, (size_t)ncoef * sizeof(double));
+    if (e == cudaSuccess) {
+        const int work = (n_knots - 1) * (degree + 1);
+        switch (degree) {
+            case 1: banded_coeff_kernel<1><<<(work + 127) / 128, 128>>>(b.t_dev, n_knots, b.coef); break;
+            case 2: banded_coeff_kernel<2><<<(work + 127) / 128, 128>>>(b.t_dev, n_knots, b.coef); break;
+            default: banded_coeff_kernel<3><<<(work + 127) / 128, 128>>>(b.t_dev, n_knots, b.coef); break;
+        }
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&b.partials, (size_t)b.nwarps * b.rec * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&b.reduced, (size_t)b.rec * sizeof(double));
+    if (e != cudaSuccess) {
+        const int code = (e == cudaErrorMemoryAllocation) ? ANML_ENOMEM : ANML_ECUDA;
+        (void)cudaGetLastError();
+        free_banded(m);
+        return fail(code, "anml_model_enable_banded_spline: %s", cudaGetErrorString(e));
+    }
+    b.gathered = false;
+    b.enabled = true;
+    return ANML_OK;
+}
+
 static int eval_on_stream(anml_model* m, const double* x_host, int want, cudaStream_t st) {
     TRY(ensure_buffers(m));
     for (int k = 0; k < m->K; ++k)
@@ -1211,7 +1375,9 @@ static int eval_on_stream(anml_model* m, const double* x_host, int want, cudaStr
     CU_TRY(cudaMemsetAsync(m->d_status, 0, sizeof(int), st));
 
     const anml_design* d0 = m->par[0].design;
-    if (m->K == 1 && d0->p <= 64 && !m->force_generic) {
+    if (m->banded.enabled && !m->force_generic) {
+        TRY(eval_banded(m, want, st));
+    } else if (m->K == 1 && d0->p <= 64 && !m->force_generic) {
         FusedArgs a;
         a.n = m->n; a.p = d0->p; a.link = m->par[0].link; a.family = m->family; a.fast = m->no_fast ? 0 : 1;
         a.beta = m->d_beta + m->par[0].pad_off; a.obs = m->obs; a.se = m->se; a.offset = m->par[0].offset; a.weights = m->weights;

@@ -96,7 +96,7 @@ __device__ __forceinline__ RowTerms1 row_terms1(int family, int link, bool fast,
         return o;
     }
     if (fast && family == FAM_GAUSSIAN && link == LINK_IDENTITY) {
-        const double is = 1.0 / se;
+        const double is = (se == 1.0) ? 1.0 : 1.0 / se;  // the default obs_se: no division
         const double iv = is * is;
         const double res = y - obs;
         o.r = res * iv;

@@ -50,6 +50,7 @@ class Model:
         self.parameters = parameters
         self.device = device
         self._native: Optional[_native.NativeModel] = None
+        self.banded_spline = False  # set by attach: the one-spline model runs on the banded evaluator
         self._cache_key = None
         self._cache = None
         self.prior_enabled = True
@@ -153,8 +154,22 @@ class Model:
                                       linear.mean if has_linear else None,
                                       linear.sd if has_linear else None)
         nm.set_prior_enabled(self.prior_enabled)
+        self.banded_spline = self._enable_banded_spline(nm)
         self._native = nm
         self._cache_key = None
+
+    # A parameter that is exactly one spline variable (BASELINE config #3) is evaluated from the
+    # abscissae, the basis computed on the fly, instead of streaming the dense design (spline_eval.cuh).
+    use_banded_spline = True
+
+    def _enable_banded_spline(self, nm) -> bool:
+        if not self.use_banded_spline or len(self.parameters) != 1 or len(self.parameters[0].variables) != 1:
+            return False
+        var = self.parameters[0].variables[0]
+        x_dev = getattr(var, "device_abscissae", None)
+        if x_dev is None or not (1 <= var.spline.degree <= 3) or x_dev.size != nm.n_rows:
+            return False
+        return nm.enable_banded_spline(var.spline.knots, var.spline.degree, x_dev_ptr=x_dev.ptr)
 
     def set_prior_enabled(self, enabled: bool) -> None:
         """Row-sharded runs keep the prior on one rank only."""

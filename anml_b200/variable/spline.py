@@ -34,6 +34,7 @@ class SplineVariable(Variable):
         super().__init__(component, priors)
         self.spline = spline
         self.last_interval_index = None
+        self.device_abscissae = None  # DeviceBuffer with the attached column, set by Parameter.attach
 
     @property
     def spline(self) -> Union[XSpline, SplineGetter]:
@@ -78,6 +79,9 @@ class SplineVariable(Variable):
 
         self.component.attach(df)
         x = _native.as_f64(self.component.value, self.component.key)
+        if self.device_abscissae is not None:
+            self.device_abscissae.free()
+            self.device_abscissae = None
         xbuf = _native.DeviceBuffer(design.device, x)
         try:
             if isinstance(self.spline, SplineGetter):
@@ -93,5 +97,8 @@ class SplineVariable(Variable):
                 raise NotImplementedError("ldegree/rdegree that change the basis count are not supported")
             self.last_interval_index = design.set_spline(col0, None, sp.knots, sp.degree, sp.ldegree or 0, sp.rdegree or 0, 0,
                                                          want_index=False, x_dev_ptr=xbuf.ptr)
-        finally:
+        except BaseException:
             xbuf.free()
+            raise
+        # kept for the model layer: a one-spline model is evaluated from the abscissae (8 bytes per row)
+        self.device_abscissae = xbuf

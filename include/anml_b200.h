@@ -124,6 +124,12 @@ int anml_model_destroy(anml_model* m);
 int anml_model_set_param(anml_model* m, int k, const anml_design* design, int link, const double* offset_dev);
 int anml_model_set_obs(anml_model* m, const double* obs, int on_device);
 int anml_model_set_obs_se(anml_model* m, const double* obs_se /* NULL = 1.0 */, int on_device);
+/* One-parameter model whose design is ONE B-spline basis (BASELINE config #3): evaluate the basis on the
+ * fly from the abscissae instead of streaming the dense (n, nb) design (csrc/spline_eval.cuh).  Call after
+ * anml_model_set_param with the dense design of the same spline (it stays the fallback and serves
+ * get_params); x holds the n abscissae (host or device; not retained).  ANML_EUNSUPPORTED when an abscissa
+ * lies outside the knot span or degree > 3: the model then keeps using the dense design. */
+int anml_model_enable_banded_spline(anml_model* m, const double* x, int x_on_device, const double* knots, int n_knots, int degree);
 /* optional per-row likelihood weights (>= 0; NULL = all ones): every row's NLL term, and
  * with it its gradient and Hessian contribution, is multiplied by its weight (trimming) */
 int anml_model_set_weights(anml_model* m, const double* weights, int on_device);

@@ -150,3 +150,97 @@ def test_spline_variable_resolves_data_dependent_knots_on_device(knots_type):
     assert par.size == 11 and par.design_mat.shape == (n, 11)
     want = O.spline_design(want_knots, 3, x)
     np.testing.assert_array_equal(par.design_mat, want)
+
+
+def _spline_model(family, n, seed, knots_type="rel_domain", with_extras=False, degree=3):
+    import pandas as pd
+
+    from anml_b200.data import Component, DataExample, DataPrototype
+    from anml_b200.getter.prior import SplinePriorGetter
+    from anml_b200.getter.spline import SplineGetter
+    from anml_b200.model import Model
+    from anml_b200.parameter import Expit, Identity, Parameter
+    from anml_b200.prior import GaussianPrior
+    from anml_b200.variable import SplineVariable
+
+    rng = np.random.default_rng(seed)
+    x = rng.beta(2.0, 3.0, size=n) * 4.0 - 1.0
+    df = pd.DataFrame({"x": x})
+    f = np.sin(1.5 * x)
+    if family == "binomial":
+        df["obs"] = (rng.uniform(size=n) < 1 / (1 + np.exp(-2 * f))).astype(float)
+    else:
+        df["obs"] = f + 0.1 * rng.normal(size=n)
+        df["obs_se"] = rng.uniform(0.5, 1.5, size=n)
+    offset = None
+    if with_extras:
+        df["off"] = 0.1 * rng.normal(size=n)
+        offset = "off"
+    var = SplineVariable("x", SplineGetter(np.linspace(0.0, 1.0, 12), degree=degree, knots_type=knots_type),
+                         priors=[SplinePriorGetter(GaussianPrior(mean=0.0, sd=2.0), size=50, order=2)])
+    par = Parameter([var], transform=Expit() if family == "binomial" else Identity(), offset=offset)
+    model = Model(family, DataExample("obs", "obs_se"), [par])
+    return model, par, var, df
+
+
+@pytest.mark.parametrize("family,extras,degree", [("gaussian", False, 3), ("gaussian", True, 2), ("binomial", True, 3), ("binomial", False, 1)])
+def test_one_spline_model_runs_on_the_banded_evaluator(family, extras, degree):
+    """BASELINE config #3 shape: the model whose only variable is a spline is evaluated from the
+    abscissae (spline_eval.cuh).  Same objective / gradient / Hessian as the dense design route
+    (tolerances of BASELINE.json) and as the oracle on the materialised basis."""
+    n = 120_007
+    model, par, var, df = _spline_model(family, n, seed=degree + 10 * extras, with_extras=extras, degree=degree)
+    model.attach(df)
+    assert model.banded_spline is True
+    nb = par.size
+    x = np.random.default_rng(5).normal(size=nb) * 0.3
+    o, g, H = model.evaluate(x)
+    assert np.array_equal(H, H.T)
+    i, j = np.indices(H.shape)
+    lin = par.prior_dict["linear"]["GaussianPrior"]
+    prior_H = (lin.mat.T / lin.params[1] ** 2) @ lin.mat
+    assert np.all((H - prior_H)[np.abs(i - j) > degree] == 0.0)  # likelihood part is banded
+    # dense design route of the same model
+    model.native.set_option("force_generic", 0)
+    model.use_banded_spline = False
+    model.attach(df)
+    assert model.banded_spline is False
+    od, gd, Hd = model.evaluate(x * (1 + 1e-16))
+    assert abs(o - od) <= 1e-12 * abs(od)
+    assert np.abs(g - gd).max() <= 1e-12 * np.abs(gd).max()
+    assert np.abs(H - Hd).max() <= 1e-12 * np.abs(Hd).max()
+    # oracle on the host basis
+    B = O.spline_design(var.spline.knots, degree, df["x"].to_numpy())
+    link = "expit" if family == "binomial" else "identity"
+    priors = [{"linear": (lin.params[0], lin.params[1], lin.mat)}]
+    want = O.model_eval_fused(family, df["obs"].to_numpy(), [B], [link], x, offsets=[df["off"].to_numpy() if extras else None],
+                              obs_se=df["obs_se"].to_numpy() if family == "gaussian" else None, priors=priors)
+    assert abs(o - want[0]) <= 1e-10 * abs(want[0])
+    assert np.abs(g - want[1]).max() <= 1e-10 * np.abs(want[1]).max()
+    assert np.abs(H - want[2]).max() <= 1e-9 * np.abs(want[2]).max()
+
+
+def test_banded_evaluator_declines_when_rows_leave_the_knot_span():
+    """Absolute knots narrower than the data: extrapolated rows are not handled by the banded
+    path, the library says so and the model stays on the dense design."""
+    import pandas as pd
+
+    from anml_b200.data import DataExample
+    from anml_b200.getter.spline import SplineGetter
+    from anml_b200.model import Model
+    from anml_b200.parameter import Parameter
+    from anml_b200.variable import SplineVariable
+
+    rng = np.random.default_rng(3)
+    n = 70_001
+    df = pd.DataFrame({"x": rng.uniform(-0.2, 1.2, size=n)})
+    df["obs"] = df["x"] ** 2 + 0.1 * rng.normal(size=n)
+    var = SplineVariable("x", SplineGetter(np.linspace(0.0, 1.0, 8), degree=3, knots_type="abs"))
+    model = Model("gaussian", DataExample("obs", "obs_se"), [Parameter([var])])
+    model.attach(df)
+    assert model.banded_spline is False
+    x = rng.normal(size=model.size)
+    B = O.spline_design(var.spline.knots, 3, df["x"].to_numpy())
+    want = O.model_eval_fused("gaussian", df["obs"].to_numpy(), [B], ["identity"], x, obs_se=np.ones(n))
+    o, g, H = model.evaluate(x)
+    assert abs(o - want[0]) <= 1e-10 * abs(want[0]) and np.abs(H - want[2]).max() <= 1e-9 * np.abs(want[2]).max()
