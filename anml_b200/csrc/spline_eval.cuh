@@ -54,7 +54,7 @@ struct BandedCfg {
 template <int DEG>
 __global__ void __launch_bounds__(256, 2) spline_banded_eval_kernel(const BandedArgs a) {
     using C = BandedCfg<DEG>;
-    extern __shared__ double sm_banded[];
+    extern __shared__ __align__(16) double sm_banded[];
     const int nt = a.nk + 2 * DEG;
     const int nb = a.nk - 1 + DEG;
     double* t_s = sm_banded;
@@ -135,9 +135,21 @@ __global__ void __launch_bounds__(256, 2) spline_banded_eval_kernel(const Banded
         const double* c = coef + idx * (DEG + 1) * (DEG + 1);
 #pragma unroll
         for (int q = 0; q <= DEG; ++q) {
-            double v = c[q * (DEG + 1) + DEG];
+            double ck[DEG + 1];
+            if ((DEG + 1) % 2 == 0) {  // coefficient rows are 16-byte aligned: 128-bit loads
 #pragma unroll
-            for (int k = DEG - 1; k >= 0; --k) v = fma(v, u, c[q * (DEG + 1) + k]);
+                for (int k = 0; k <= DEG; k += 2) {
+                    const double2 v2 = *reinterpret_cast<const double2*>(c + q * (DEG + 1) + k);
+                    ck[k] = v2.x;
+                    ck[k + 1] = v2.y;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k <= DEG; ++k) ck[k] = c[q * (DEG + 1) + k];
+            }
+            double v = ck[DEG];
+#pragma unroll
+            for (int k = DEG - 1; k >= 0; --k) v = fma(v, u, ck[k]);
             N[q] = v;
         }
         double y = in.off;
@@ -157,7 +169,24 @@ __global__ void __launch_bounds__(256, 2) spline_banded_eval_kernel(const Banded
         }
     };
     // lanes of one interval accumulate together; the warp walks the (few) distinct intervals in order
+    auto add_row = [&](const double* N, double rr, double ww) {
+#pragma unroll
+        for (int q = 0; q <= DEG; ++q) accG[q] = fma(rr, N[q], accG[q]);
+        if (a.want_hess) {
+#pragma unroll
+            for (int p = 0; p <= DEG; ++p) {
+                const double wp = ww * N[p];
+#pragma unroll
+                for (int q = 0; q <= p; ++q) accH[p * (p + 1) / 2 + q] = fma(wp, N[q], accH[p * (p + 1) / 2 + q]);
+            }
+        }
+    };
     auto accumulate = [&](bool active, int idx, const double* N, double rr, double ww) {
+        // common case: every active lane is still in the warp's current interval
+        if (__all_sync(FULL_MASK, !active || idx == cur)) {
+            if (active) add_row(N, rr, ww);
+            return;
+        }
         unsigned todo = __ballot_sync(FULL_MASK, active);
         while (todo) {
             const int leader = __ffs(todo) - 1;
@@ -167,18 +196,7 @@ __global__ void __launch_bounds__(256, 2) spline_banded_eval_kernel(const Banded
                 if (cur >= 0) flush();
                 cur = v;
             }
-            if (mine) {
-#pragma unroll
-                for (int q = 0; q <= DEG; ++q) accG[q] = fma(rr, N[q], accG[q]);
-                if (a.want_hess) {
-#pragma unroll
-                    for (int p = 0; p <= DEG; ++p) {
-                        const double wp = ww * N[p];
-#pragma unroll
-                        for (int q = 0; q <= p; ++q) accH[p * (p + 1) / 2 + q] = fma(wp, N[q], accH[p * (p + 1) / 2 + q]);
-                    }
-                }
-            }
+            if (mine) add_row(N, rr, ww);
             todo &= ~__ballot_sync(FULL_MASK, mine);
         }
     };
