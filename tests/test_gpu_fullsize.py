@@ -133,6 +133,15 @@ def test_config3_spline_50m_rows_partition_of_unity_and_indices():
     i, j = np.indices(H0.shape)
     assert np.all(H0[np.abs(i - j) > deg] == 0.0) and np.all(np.diag(H0) > 0)
     assert abs(H0.sum() - n) <= 1e-10 * n  # sum_ij H_ij = sum_rows (sum_j B_j)^2 = n
+    # the banded evaluator (basis on the fly from the sorted abscissae) on the same 5e7 rows
+    assert m.enable_banded_spline(knots, deg, x_dev_ptr=xs.data_ptr()) is True
+    ob, gb, Hb = m.eval(np.linspace(-1, 1, nb))
+    ob2, gb2, Hb2 = m.eval(np.linspace(-1, 1, nb))
+    assert ob == ob2 and np.array_equal(gb, gb2) and np.array_equal(Hb, Hb2)  # bitwise reproducible
+    assert abs(ob - o1) <= 1e-12 * abs(o1)
+    assert np.abs(gb - g1).max() <= 1e-12 * np.abs(g1).max()
+    assert np.abs(Hb - H1).max() <= 1e-12 * np.abs(H1).max()
+    assert np.array_equal(Hb, Hb.T) and np.all(Hb[np.abs(i - j) > deg] == 0.0)
     assert abs(o0 - 0.5 * float((obs**2).sum())) <= 1e-12 * o0
 
 
