@@ -1254,11 +1254,20 @@ static int eval_banded(anml_model* m, int want, cudaStream_t st) {
     const size_t smem = (size_t)(((b.nk + 2 * b.degree + 1) & ~1) + ((b.nb + 1) & ~1)) * sizeof(double) + (a.coef_in_smem ? coef_bytes : 0);
     EventPair* ep = next_events(m);
     if (ep) CU_TRY(cudaEventRecord(ep->a, st));
-    switch (b.degree) {
-        case 1: spline_banded_eval_kernel<1><<<grid, 256, smem, st>>>(a); break;
-        case 2: spline_banded_eval_kernel<2><<<grid, 256, smem, st>>>(a); break;
-        default: spline_banded_eval_kernel<3><<<grid, 256, smem, st>>>(a); break;
+#define BANDED_LAUNCH(D)                                                                          \
+    if (a.coef_in_smem) {                                                                         \
+        if (hess) spline_banded_eval_kernel<D, true, true><<<grid, 256, smem, st>>>(a);           \
+        else spline_banded_eval_kernel<D, true, false><<<grid, 256, smem, st>>>(a);               \
+    } else {                                                                                      \
+        if (hess) spline_banded_eval_kernel<D, false, true><<<grid, 256, smem, st>>>(a);          \
+        else spline_banded_eval_kernel<D, false, false><<<grid, 256, smem, st>>>(a);              \
     }
+    switch (b.degree) {
+        case 1: BANDED_LAUNCH(1) break;
+        case 2: BANDED_LAUNCH(2) break;
+        default: BANDED_LAUNCH(3) break;
+    }
+#undef BANDED_LAUNCH
     CU_TRY(cudaGetLastError());
     if (ep) CU_TRY(cudaEventRecord(ep->b, st));
     banded_reduce_kernel<<<(b.rec + 31) / 32, dim3(32, 32), 0, st>>>(b.partials, b.nwarps, b.rec, b.reduced);

@@ -51,7 +51,9 @@ struct BandedCfg {
     static constexpr int SLOTS = NG + NH;  // per interval: gradient entries, then the lower triangle row by row
 };
 
-template <int DEG>
+// COEF_SMEM: the coefficient table fits in shared memory (LDS.128 instead of generic loads);
+// HESS: the Hessian band is wanted -- both compile-time, the row loop is bound by instruction issue.
+template <int DEG, bool COEF_SMEM, bool HESS>
 __global__ void __launch_bounds__(256, 2) spline_banded_eval_kernel(const BandedArgs a) {
     using C = BandedCfg<DEG>;
     extern __shared__ __align__(16) double sm_banded[];
@@ -62,11 +64,11 @@ __global__ void __launch_bounds__(256, 2) spline_banded_eval_kernel(const Banded
     double* coef_s = beta_s + ((nb + 1) & ~1);
     for (int i = threadIdx.x; i < nt; i += blockDim.x) t_s[i] = a.t[i];
     for (int i = threadIdx.x; i < nb; i += blockDim.x) beta_s[i] = a.beta[i];
-    if (a.coef_in_smem)
+    if (COEF_SMEM)
         for (int i = threadIdx.x; i < (a.nk - 1) * (DEG + 1) * (DEG + 1); i += blockDim.x) coef_s[i] = a.coef[i];
     __syncthreads();
     const double* knots = t_s + DEG;
-    const double* coef = a.coef_in_smem ? coef_s : a.coef;
+    const uint32_t coef_u32 = smem_u32(coef_s);
 
     const int lane = threadIdx.x & 31;
     const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(256, 2) spline_banded_eval_kernel(const Banded
             if (lane == q) mine = v;
             accG[q] = 0.0;
         }
-        if (a.want_hess) {
+        if (HESS) {
 #pragma unroll
             for (int q = 0; q < C::NH; ++q) {
                 const double v = warp_sum(accH[q]);
@@ -124,28 +126,27 @@ __global__ void __launch_bounds__(256, 2) spline_banded_eval_kernel(const Banded
         return r;
     };
     auto compute = [&](const RowIn& in, bool active, int& idx, double* N, double& rr, double& ww) {
-        rr = 0.0;
-        ww = 0.0;
-#pragma unroll
-        for (int q = 0; q <= DEG; ++q) N[q] = 0.0;
-        if (!active) return;
+        if (!active) return;  // N, rr, ww of an inactive lane are never read
         const double x = in.x;
         while (idx < a.nk - 2 && knots[idx + 1] <= x) ++idx;
         const double u = x - knots[idx];
-        const double* c = coef + idx * (DEG + 1) * (DEG + 1);
+        const int cbase = idx * (DEG + 1) * (DEG + 1);
 #pragma unroll
         for (int q = 0; q <= DEG; ++q) {
             double ck[DEG + 1];
-            if ((DEG + 1) % 2 == 0) {  // coefficient rows are 16-byte aligned: 128-bit loads
+            if (COEF_SMEM && (DEG + 1) % 2 == 0) {  // coefficient rows are 16-byte aligned: LDS.128
 #pragma unroll
                 for (int k = 0; k <= DEG; k += 2) {
-                    const double2 v2 = *reinterpret_cast<const double2*>(c + q * (DEG + 1) + k);
+                    const double2 v2 = lds128(coef_u32 + (cbase + q * (DEG + 1) + k) * 8);
                     ck[k] = v2.x;
                     ck[k + 1] = v2.y;
                 }
+            } else if (COEF_SMEM) {
+#pragma unroll
+                for (int k = 0; k <= DEG; ++k) ck[k] = lds64(coef_u32 + (cbase + q * (DEG + 1) + k) * 8);
             } else {
 #pragma unroll
-                for (int k = 0; k <= DEG; ++k) ck[k] = c[q * (DEG + 1) + k];
+                for (int k = 0; k <= DEG; ++k) ck[k] = __ldg(a.coef + cbase + q * (DEG + 1) + k);
             }
             double v = ck[DEG];
 #pragma unroll
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(256, 2) spline_banded_eval_kernel(const Banded
     auto add_row = [&](const double* N, double rr, double ww) {
 #pragma unroll
         for (int q = 0; q <= DEG; ++q) accG[q] = fma(rr, N[q], accG[q]);
-        if (a.want_hess) {
+        if (HESS) {
 #pragma unroll
             for (int p = 0; p <= DEG; ++p) {
                 const double wp = ww * N[p];
