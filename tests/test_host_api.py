@@ -314,3 +314,21 @@ def test_component_attaches_to_a_pyarrow_table():
     assert "intercept" in frame and "intercept" not in table.column_names
     with pytest.raises(KeyError):
         Component("missing").attach(frame)
+
+
+def test_quantile_interpolation_restatement_matches_numpy(monkeypatch):
+    """The host half of the device quantiles (anml_b200._native.vector_quantile): virtual index,
+    neighbour ranks and NumPy's lerp, with the device order statistics replaced by a host sort."""
+    from anml_b200 import _native as N
+
+    rng = np.random.default_rng(4)
+    for n in (1, 2, 3, 10, 1001, 65537):
+        x = np.round(rng.normal(size=n) * 5.0, 2)  # ties
+        srt = np.sort(x)
+        monkeypatch.setattr(N, "vector_minmax", lambda x_=None, dev_ptr=None, n=None, device=0, _s=srt: (float(_s[0]), float(_s[-1])))
+        monkeypatch.setattr(N, "vector_order_stats", lambda ranks, x_=None, dev_ptr=None, n=None, device=0, _s=srt: _s[np.asarray(ranks)])
+        q = np.concatenate([np.linspace(0, 1, 23), rng.uniform(size=40), [0.5, 1 / 3, 2 / 3, 1e-12, 1 - 1e-12]])
+        np.testing.assert_array_equal(N.vector_quantile(q, x), np.quantile(x, q))
+        np.testing.assert_array_equal(N.vector_quantile(q.reshape(4, -1), x), np.quantile(x, q.reshape(4, -1)))
+    with pytest.raises(ValueError):
+        N.vector_quantile([-0.1], np.arange(3.0))
