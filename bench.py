@@ -74,6 +74,19 @@ def cpu_threads():
     return os.cpu_count() or 1, "blas"
 
 
+def all_blas_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arms are meant to use every host
+    core, so lift the BLAS pool back to os.cpu_count() for their duration."""
+    try:
+        from threadpoolctl import threadpool_limits
+
+        return threadpool_limits(limits=os.cpu_count() or 1, user_api="blas")
+    except Exception:
+        import contextlib
+
+        return contextlib.nullcontext()
+
+
 def cpu_eval_seconds(X, obs, x, p, reps, warmup=1):
     from oracle import anml_oracle as O
 
@@ -110,10 +123,11 @@ def run_reference(args):
     n_total, p = args.rows, args.p
     n_sample = min(n_total, args.cpu_rows)
     X, obs, beta_true = cpu_sample(n_sample, p, SEED + 2)
-    times = cpu_eval_seconds(X, obs, 0.5 * beta_true, p, reps=args.steps, warmup=args.warmup)
+    with all_blas_threads():
+        times = cpu_eval_seconds(X, obs, 0.5 * beta_true, p, reps=args.steps, warmup=args.warmup)
+        cores, api = cpu_threads()
     sec = float(np.mean(times))
     value = (n_sample / sec) / n_total
-    cores, api = cpu_threads()
     sample = (f"{n_sample} of {n_total} rows per step, evals/s extrapolated linearly in rows; NumPy {np.__version__} "
               f"({api}, {cores} threads of {os.cpu_count()} cores); row chunks of 262144")
     line = {
@@ -391,9 +405,10 @@ def run_gpu(args):
                 line["ingest"] = {"error": repr(exc)}
             n_sample = min(n_total, args.cpu_rows)
             Xc, oc, bt = cpu_sample(n_sample, p, SEED + 2)
-            times = cpu_eval_seconds(Xc, oc, 0.5 * bt, p, reps=3, warmup=1)
+            with all_blas_threads():
+                times = cpu_eval_seconds(Xc, oc, 0.5 * bt, p, reps=3, warmup=1)
+                cores, api = cpu_threads()
             sec = float(min(times))
-            cores, api = cpu_threads()
             line["cpu_baseline"] = {
                 "value": (n_sample / sec) / n_total, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": f"{n_sample} of {n_total} rows, best of 3, evals/s extrapolated linearly in rows; NumPy oracle route "
@@ -402,7 +417,8 @@ def run_gpu(args):
             # the reference's literal route (get_params order 2 materialises an (n,p,p) tensor,
             # parameter/main.py:278-280) at the largest n whose tensor stays under ~1 GB
             n_lit = max(16, min(n_sample, int(1e9 / (8.0 * p * p))))
-            line["cpu_baseline"]["literal_route"] = cpu_literal_rows_per_s(Xc[:n_lit], oc[:n_lit], 0.5 * bt, p)
+            with all_blas_threads():
+                line["cpu_baseline"]["literal_route"] = cpu_literal_rows_per_s(Xc[:n_lit], oc[:n_lit], 0.5 * bt, p)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
