@@ -195,3 +195,81 @@ class ShardedModel:
             return minimize(self.objective, x0, jac=self.gradient, hess=self.hessian, method="trust-constr", options=opts, **kwargs)
         finally:
             self.stop()
+
+
+# ---- data-dependent spline knots on sharded data -------------------------------------------
+def resolve_sharded_spline_knots(parameters, df, group=None) -> int:
+    """Give every rank the knots the *whole* data set would produce.
+
+    A ``SplineGetter`` with ``knots_type='rel_domain'`` / ``'rel_freq'`` places its knots from
+    the column it is attached to (getter/spline.py:92-99).  On row shards that would differ from
+    rank to rank, and the per-rank Hessians would not be blocks of one model.  Call this on every
+    rank *before* ``attach`` with the rank's own frame: ``rel_domain`` knots come from an
+    all-reduce(MIN/MAX) of the column range, ``rel_freq`` knots from the quantiles of the column
+    gathered on rank 0 (8 bytes per row, once) and broadcast; the getters are replaced in place by
+    the resolved ``XSpline`` (as the first ``attach`` would do, variable/spline.py:103-107).
+    Returns the number of variables resolved.  Without an initialised process group it resolves
+    against the local frame only.
+    """
+    import torch
+    import torch.distributed as dist
+
+    from .data.frame import as_frame
+    from .getter.spline import SplineGetter
+    from .variable.spline import SplineVariable
+    from .xspline import XSpline
+
+    df = as_frame(df)
+    live = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if live else 1
+    rank = dist.get_rank(group) if live else 0
+    on_gpu = live and dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+
+    def quantiles(values: np.ndarray, q) -> np.ndarray:
+        if on_gpu and values.size >= (1 << 16):
+            from . import _native
+
+            return _native.vector_quantile(q, values, device=dev.index)
+        return np.quantile(values, q)
+
+    resolved = 0
+    for par in parameters:
+        for var in par.variables:
+            if not isinstance(var, SplineVariable) or not isinstance(var.spline, SplineGetter):
+                continue
+            getter = var.spline
+            if getter.knots_type == "abs":
+                continue
+            var.component.attach(df)
+            col = np.ascontiguousarray(var.component.value, dtype=np.float64)
+            if getter.knots_type == "rel_domain":
+                # empty shards must not win the reduction
+                lo = col.min() if col.size else np.inf
+                hi = col.max() if col.size else -np.inf
+                ends = torch.tensor([lo, -hi], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(ends, op=dist.ReduceOp.MIN, group=group)
+                lo, hi = np.float64(ends[0].item()), np.float64(-ends[1].item())
+                knots = lo + np.asarray(getter.knots) * (hi - lo)
+            else:  # rel_freq: exact quantiles of the union of the shards
+                if world > 1:
+                    sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+                    sizes[rank] = col.size
+                    dist.all_reduce(sizes, group=group)
+                    longest = int(sizes.max().item())
+                    mine = torch.full((longest,), float("nan"), dtype=torch.float64, device=dev)
+                    mine[: col.size] = torch.from_numpy(col).to(dev)
+                    parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+                    dist.gather(mine, parts, dst=0, group=group)
+                    kn = torch.empty(len(getter.knots), dtype=torch.float64, device=dev)
+                    if rank == 0:
+                        full = np.concatenate([parts[r][: int(sizes[r].item())].cpu().numpy() for r in range(world)])
+                        kn.copy_(torch.from_numpy(np.asarray(quantiles(full, getter.knots), dtype=np.float64)))
+                    dist.broadcast(kn, src=0, group=group)
+                    knots = kn.cpu().numpy()
+                else:
+                    knots = quantiles(col, getter.knots)
+            var.spline = XSpline(knots, getter.degree, ldegree=getter.ldegree, rdegree=getter.rdegree)
+            resolved += 1
+    return resolved

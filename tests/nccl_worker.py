@@ -65,6 +65,34 @@ def main():
         dist.broadcast(ref0, src=0)
         assert torch.equal(mine, ref0)
 
+        # ---- a sharded one-spline model: knots of the whole data set on every rank, banded evaluator per shard
+        from anml_b200.distributed import resolve_sharded_spline_knots
+        from anml_b200.getter.spline import SplineGetter
+        from anml_b200.parameter import Identity
+        from anml_b200.variable import SplineVariable
+
+        xs_full = rng.gamma(2.0, 1.0, size=n)
+        ys_full = np.sin(xs_full) + 0.1 * rng.normal(size=n)
+        for kt in ("rel_domain", "rel_freq"):
+            fractions = np.linspace(0.0, 1.0, 9)
+            svar = SplineVariable("xs", SplineGetter(fractions, degree=3, knots_type=kt))
+            spar = Parameter([svar], transform=Identity(), device=local_rank)
+            sdf = pd.DataFrame({"xs": xs_full[lo:hi], "obs": ys_full[lo:hi]})
+            assert resolve_sharded_spline_knots([spar], sdf) == 1
+            want_knots = (xs_full.min() + fractions * (xs_full.max() - xs_full.min())) if kt == "rel_domain" else np.quantile(xs_full, fractions)
+            assert np.array_equal(svar.spline.knots, want_knots)
+            smodel = Model("gaussian", DataExample("obs", "obs_se"), [spar], device=local_rank)
+            smodel.attach(sdf)
+            assert smodel.banded_spline is True
+            ssh = ShardedModel(NativeLocalEvaluator(smodel, torch.device("cuda", local_rank)))
+            bx = np.linspace(-1.0, 1.0, spar.size)
+            so, sg, sh = ssh.unpack(ssh.evaluate_collective(bx, True))
+            B = O.spline_design(want_knots, 3, xs_full)
+            sw = O.model_eval_fused("gaussian", ys_full, [B], ["identity"], bx, obs_se=np.ones(n))
+            assert abs(so - sw[0]) <= 1e-10 * abs(sw[0])
+            assert np.abs(sg - sw[1]).max() <= 1e-10 * np.abs(sw[1]).max()
+            assert np.abs(sh - sw[2]).max() <= 1e-9 * np.abs(sw[2]).max()
+
         res = sharded.fit(np.zeros(p), options={"gtol": 1e-10})
         if rank == 0:
             from scipy.optimize import minimize

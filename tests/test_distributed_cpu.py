@@ -102,3 +102,57 @@ def test_two_rank_gloo_sharded_fit():
         p.join(timeout=60)
     assert all(r[0] == "ok" for r in results), results
     assert max(r[1] for r in results) > 3
+
+
+def _knots_worker(rank, world, port, out):
+    import pandas as pd
+    import torch.distributed as dist
+
+    from anml_b200.distributed import resolve_sharded_spline_knots
+    from anml_b200.getter.spline import SplineGetter
+    from anml_b200.parameter import Parameter
+    from anml_b200.variable import SplineVariable
+    from anml_b200.xspline import XSpline
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(31)
+        full = np.round(rng.gamma(2.0, 1.0, size=10_001), 3)
+        lo, hi = shard_rows(full.size, world, rank)
+        df = pd.DataFrame({"x": full[lo:hi], "z": -full[lo:hi]})
+        fractions = np.linspace(0.0, 1.0, 7)
+        va = SplineVariable("x", SplineGetter(fractions, degree=3, knots_type="rel_domain"))
+        vb = SplineVariable("z", SplineGetter(fractions, degree=2, knots_type="rel_freq"))
+        vc = SplineVariable("x", SplineGetter(np.array([0.0, 1.0, 20.0]), degree=1, knots_type="abs"))
+        n = resolve_sharded_spline_knots([Parameter([va, vb]), Parameter([vc])], df)
+        assert n == 2 and isinstance(va.spline, XSpline) and isinstance(vb.spline, XSpline)
+        assert isinstance(vc.spline, SplineGetter)  # absolute knots need no data
+        want_a = full.min() + fractions * (full.max() - full.min())
+        want_b = np.quantile(-full, fractions)
+        assert np.array_equal(va.spline.knots, want_a), (va.spline.knots, want_a)
+        assert np.array_equal(vb.spline.knots, want_b), (vb.spline.knots, want_b)
+        assert vb.spline.degree == 2
+        out.put(("ok", rank))
+    except Exception as e:  # pragma: no cover
+        out.put(("fail", repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_spline_knots_are_those_of_the_whole_data_set():
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_knots_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[0] == "ok" for r in results), results
