@@ -171,7 +171,11 @@ static cudaError_t upload_run(int device, int sm_count, const UploadJob& job) {
     } else {
         std::vector<std::thread> threads;
         threads.reserve(nthreads - 1);
-        for (int t = 1; t < nthreads; ++t) threads.emplace_back(work, t);
+        try {
+            for (int t = 1; t < nthreads; ++t) threads.emplace_back(work, t);
+        } catch (...) {
+            // thread creation refused (resource limits): the lanes that did start plus this thread share the chunks
+        }
         work(0);
         for (auto& t : threads) t.join();
     }
