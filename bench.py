@@ -432,7 +432,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=lambda s: int(float(s)), default=N_TOTAL, help="total rows over all GPUs")
     ap.add_argument("--p", type=int, default=P)
-    ap.add_argument("--cpu-rows", type=lambda s: int(float(s)), default=4_000_000, help="rows of the bounded CPU sample")
+    ap.add_argument("--cpu-rows", type=lambda s: int(float(s)), default=8_000_000, help="rows of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
