@@ -13,7 +13,8 @@ import threading
 import numpy as np
 
 _LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
-LIB_PATH = os.path.join(_LIB_DIR, "libanml_b200.so")
+# ANML_B200_LIB: another build of the same library (kernel A/B experiments, tools/run_variants.sh)
+LIB_PATH = os.environ.get("ANML_B200_LIB") or os.path.join(_LIB_DIR, "libanml_b200.so")
 
 OK, EINVAL, ECUDA, ENOMEM, ESTATE, EUNSUPPORTED, EDOMAIN = range(7)
 
@@ -37,7 +38,10 @@ SIGNATURES = {
     "anml_dev_free": (C.c_int, [C.c_int, C.c_void_p]),
     "anml_dev_upload": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64]),
     "anml_dev_download": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64]),
+    "anml_upload_release": (C.c_int, [C.c_int]),
     "anml_design_create": (C.c_int, [C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_void_p)]),
+    "anml_design_create_deferred": (C.c_int, [C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_void_p)]),
+    "anml_design_is_materialized": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "anml_design_wrap_device": (C.c_int, [C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]),
     "anml_design_destroy": (C.c_int, [C.c_void_p]),
     "anml_design_shape": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_void_p)]),
@@ -63,6 +67,13 @@ SIGNATURES = {
     "anml_model_eval_async": (C.c_int, [C.c_void_p, _c_double_p, C.c_int, C.c_void_p, C.c_void_p]),
     "anml_model_kernel_time": (C.c_int, [C.c_void_p, C.c_int, _c_double_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "anml_model_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "anml_comm_handle_bytes": (C.c_int, [C.POINTER(C.c_int)]),
+    "anml_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
+    "anml_comm_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "anml_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "anml_comm_allreduce_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "anml_comm_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "anml_comm_destroy": (C.c_int, [C.c_void_p]),
 }
 
 
@@ -161,13 +172,16 @@ class DeviceBuffer:
 class Design:
     """Row-major FP64 design matrix resident in HBM (``anml_design``)."""
 
-    def __init__(self, n_rows: int, n_cols: int, device: int = 0, _wrap=None):
+    def __init__(self, n_rows: int, n_cols: int, device: int = 0, _wrap=None, deferred: bool = False):
         require_device(device)
         self.device = device
         self.n_rows = int(n_rows)
         self.n_cols = int(n_cols)
         h = C.c_void_p()
-        if _wrap is None:
+        if deferred:
+            # nothing allocated until something needs the dense matrix (include/anml_b200.h)
+            check(load().anml_design_create_deferred(device, self.n_rows, self.n_cols, C.byref(h)))
+        elif _wrap is None:
             check(load().anml_design_create(device, self.n_rows, self.n_cols, C.byref(h)))
         else:
             ptr, ld = _wrap
@@ -201,8 +215,10 @@ class Design:
     def set_columns_device(self, col0: int, ncols: int, dev_ptr: int, src_ld: int):
         check(load().anml_design_set_columns(self.handle, col0, ncols, C.c_void_p(int(dev_ptr)), src_ld, 1))
 
-    def set_spline(self, col0, x, knots, degree, ldegree=0, rdegree=0, order=0, want_index=False, x_dev_ptr=None):
+    def set_spline(self, col0, x, knots, degree, ldegree=0, rdegree=0, order=0, want_index=False, x_dev_ptr=None, keepalive=None):
         knots = as_f64(knots, "knots")
+        if keepalive is not None:  # a deferred design borrows the abscissae until it is materialised
+            self._borrowed = getattr(self, "_borrowed", []) + [keepalive]
         idx = np.empty(self.n_rows, dtype=np.int32) if want_index else None
         idx_p = idx.ctypes.data_as(_c_int32_p) if want_index else None
         if x_dev_ptr is not None:
@@ -215,6 +231,12 @@ class Design:
         check(load().anml_design_set_spline(self.handle, col0, xp, on_dev, dptr(knots), knots.size, int(degree),
                                             int(ldegree or 0), int(rdegree or 0), int(order), idx_p))
         return idx
+
+    @property
+    def materialized(self) -> bool:
+        out = C.c_int(0)
+        check(load().anml_design_is_materialized(self.handle, C.byref(out)))
+        return bool(out.value)
 
     def validate_columns(self, col0: int, ncols: int) -> np.ndarray:
         """Per-column flags from the device validators: bit 0 = has NaN, bit 1 = has a value <= 0."""
@@ -474,3 +496,63 @@ class NativeModel:
             self.free()
         except Exception:
             pass
+
+
+class PeerComm:
+    """``anml_comm``: all-reduce of the packed record over peer memory (one launch per evaluation)."""
+
+    def __init__(self, device: int, rank: int, world: int, max_elems: int):
+        require_device(device)
+        self.device, self.rank, self.world, self.max_elems = device, rank, world, int(max_elems)
+        h = C.c_void_p()
+        check(load().anml_comm_create(device, rank, world, self.max_elems, C.byref(h)))
+        self.handle = h
+
+    @staticmethod
+    def handle_bytes() -> int:
+        n = C.c_int(0)
+        check(load().anml_comm_handle_bytes(C.byref(n)))
+        return n.value
+
+    def export(self) -> bytes:
+        buf = C.create_string_buffer(self.handle_bytes())
+        check(load().anml_comm_export(self.handle, buf))
+        return buf.raw
+
+    def connect(self, all_handles: bytes):
+        if len(all_handles) != self.world * self.handle_bytes():
+            raise ValueError("need one exported handle per rank, in rank order")
+        check(load().anml_comm_connect(self.handle, C.c_char_p(all_handles)))
+
+    def allreduce_async(self, dev_ptr: int, n_elems: int, stream_ptr: int = 0):
+        check(load().anml_comm_allreduce_async(self.handle, C.c_void_p(int(dev_ptr)), int(n_elems),
+                                               C.c_void_p(int(stream_ptr)) if stream_ptr else None))
+
+    def failed_epoch(self) -> int:
+        v = C.c_int64(0)
+        check(load().anml_comm_error(self.handle, C.byref(v)))
+        return v.value
+
+    def free(self):
+        if getattr(self, "handle", None) is not None and _lib is not None:
+            _lib.anml_comm_destroy(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _release_upload_lanes():
+    if _lib is not None:
+        try:
+            _lib.anml_upload_release(-1)
+        except Exception:
+            pass
+
+
+import atexit  # noqa: E402
+
+atexit.register(_release_upload_lanes)

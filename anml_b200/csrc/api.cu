@@ -15,7 +15,9 @@
 #include <vector>
 
 #include "../../include/anml_b200.h"
+#include "comm.cuh"
 #include "fused_eval.cuh"
+#include "finish.cuh"
 #include "fused_hess.cuh"
 #include "generic.cuh"
 #include "spline.cuh"
@@ -77,6 +79,17 @@ struct anml_design {
     CUtensorMap tmap3d64;  // box 16 x 64 x p/16
     bool has64 = false, has3d64 = false;
     int sm_count = 0;
+    // deferred build (anml_design_create_deferred): X is allocated, and the recorded spline blocks are
+    // evaluated, the first time something needs the dense matrix.  A one-spline model on the banded
+    // evaluator never does, so BASELINE config #3 no longer carries an 8.8 GB design it does not read.
+    bool deferred = false;
+    struct PendingSpline {
+        int col0;
+        const double* x_dev;  // borrowed: the caller keeps the abscissae alive as long as the design
+        std::vector<double> knots;
+        int degree, ldegree, rdegree, order;
+    };
+    std::vector<PendingSpline> pending;
 };
 
 struct PriorStore {
@@ -120,11 +133,16 @@ struct anml_model {
     int beta_len = 0;
     double *d_beta = nullptr, *h_beta = nullptr;
     double *d_packed = nullptr, *h_packed = nullptr;
-    double *d_partials = nullptr, *d_reduced = nullptr;
+    double* d_partials = nullptr;
     long long partials_len = 0;
     int* d_status = nullptr;
     cudaEvent_t beta_copied = nullptr;  // guards reuse of h_beta across async evaluations
     bool beta_pending = false;
+    // end of the last evaluation: anml_model_eval_async may run on a caller's stream, while the setters and
+    // the synchronous evaluation use the model's own -- they order themselves behind this event
+    cudaEvent_t eval_done = nullptr;
+    bool eval_pending = false;
+    cudaStream_t last_stream = nullptr;
     // general-path vectors
     double* vec[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // y0 y1 r0 r1 w00 w01 w11
     double* d_wide = nullptr;
@@ -132,9 +150,10 @@ struct anml_model {
     // banded spline evaluator (spline_eval.cuh): rows sorted by x, per-row vectors gathered into that order
     struct Banded {
         bool enabled = false, gathered = false;
-        int nk = 0, degree = 0, nb = 0, rec = 0;
-        long long nwarps = 0, rows_per_warp = 0;
+        int nk = 0, degree = 0, nb = 0, rec = 0, grid = 0;
+        long long rows_per_cta = 0;
         double *xs = nullptr, *t_dev = nullptr, *coef = nullptr, *partials = nullptr, *reduced = nullptr;
+        long long* seg = nullptr;  // first sorted row of every knot interval
         int32_t* perm = nullptr;
         double *obs_s = nullptr, *se_s = nullptr, *off_s = nullptr, *w_s = nullptr;
     } banded;
@@ -193,6 +212,14 @@ extern "C" int anml_dev_upload(int device, void* dst, const void* src, int64_t b
         return ANML_OK;
     }
     CU_TRY(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyHostToDevice));
+    return ANML_OK;
+}
+extern "C" int anml_upload_release(int device) {
+    if (device < 0) {
+        for (int d = 0; d < UPLOAD_MAX_DEVICES; ++d) upload_release_device(d);
+    } else {
+        upload_release_device(device);
+    }
     return ANML_OK;
 }
 extern "C" int anml_dev_download(int device, void* dst, const void* src, int64_t bytes) {
@@ -276,6 +303,62 @@ static int design_finish(anml_design* d) {
     return encode_design_tmap(d);
 }
 
+static int run_spline(int device, int sm_count, const double* x_dev, long long n, const double* knots, int nk, int degree,
+                      int ldegree, int rdegree, int order, double* out_dev, long long ld, int col0, int32_t* idx_dev);
+
+// a deferred design becomes a real one: allocate, encode the tensor maps, run the recorded spline blocks
+static int design_materialize(anml_design* d) {
+    if (!d || !d->deferred || d->X) return ANML_OK;
+    CU_TRY(cudaSetDevice(d->device));
+    const size_t bytes = (size_t)(d->n > 0 ? d->n : 1) * d->ld * sizeof(double);
+    cudaError_t e = cudaMalloc(&d->X, bytes);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        d->X = nullptr;
+        return fail(ANML_ENOMEM, "cudaMalloc of %zu bytes for the design matrix failed: %s", bytes, cudaGetErrorString(e));
+    }
+    d->owned = true;
+    e = cudaMemset(d->X, 0, bytes);
+    int rc = (e == cudaSuccess) ? encode_design_tmap(d) : fail(ANML_ECUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+    for (size_t i = 0; rc == ANML_OK && i < d->pending.size(); ++i) {
+        const anml_design::PendingSpline& ps = d->pending[i];
+        rc = run_spline(d->device, d->sm_count, ps.x_dev, d->n, ps.knots.data(), (int)ps.knots.size(), ps.degree, ps.ldegree, ps.rdegree,
+                        ps.order, d->X, d->ld, ps.col0, nullptr);
+    }
+    if (rc != ANML_OK) {
+        cudaFree(d->X);
+        d->X = nullptr;
+        return rc;
+    }
+    d->pending.clear();
+    return ANML_OK;
+}
+
+extern "C" int anml_design_create_deferred(int device, int64_t n_rows, int n_cols, anml_design** out) {
+    if (!out || n_rows < 0 || n_cols <= 0) return fail(ANML_EINVAL, "anml_design_create_deferred: need n_rows >= 0 and n_cols > 0");
+    if (n_rows > 2147483000LL) return fail(ANML_EUNSUPPORTED, "anml_design_create_deferred: at most 2^31 rows per device");
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(ANML_EUNSUPPORTED, "anml_b200 needs an sm_100 (B200) device, found sm_%d%d", prop.major, prop.minor);
+    anml_design* d = new (std::nothrow) anml_design();
+    if (!d) return fail(ANML_ENOMEM, "out of host memory");
+    d->device = device;
+    d->n = n_rows;
+    d->p = n_cols;
+    d->ld = round_up(n_cols, 2);
+    d->deferred = true;
+    d->sm_count = prop.multiProcessorCount;
+    *out = d;
+    return ANML_OK;
+}
+
+extern "C" int anml_design_is_materialized(const anml_design* d, int* out) {
+    if (!d || !out) return fail(ANML_EINVAL, "NULL argument");
+    *out = d->X != nullptr ? 1 : 0;
+    return ANML_OK;
+}
+
 extern "C" int anml_design_create(int device, int64_t n_rows, int n_cols, anml_design** out) {
     if (!out || n_rows < 0 || n_cols <= 0) return fail(ANML_EINVAL, "anml_design_create: need n_rows >= 0 and n_cols > 0");
     if (n_rows > 2147483000LL) return fail(ANML_EUNSUPPORTED, "anml_design_create: at most 2^31 rows per device");
@@ -345,7 +428,10 @@ extern "C" int anml_design_shape(const anml_design* d, int64_t* n_rows, int* n_c
     if (n_rows) *n_rows = d->n;
     if (n_cols) *n_cols = d->p;
     if (ld) *ld = d->ld;
-    if (dev) *dev = d->X;
+    if (dev) {
+        TRY(design_materialize(const_cast<anml_design*>(d)));
+        *dev = d->X;
+    }
     return ANML_OK;
 }
 
@@ -362,6 +448,7 @@ extern "C" int anml_design_set_columns(anml_design* d, int col0, int ncols, cons
     if (col0 < 0 || ncols <= 0 || col0 + ncols > d->p || src_ld < ncols) return fail(ANML_EINVAL, "anml_design_set_columns: columns [%d, %d) outside the %d-column design or src_ld too small", col0, col0 + ncols, d->p);
     if (d->n == 0) return ANML_OK;
     CU_TRY(cudaSetDevice(d->device));
+    TRY(design_materialize(d));
     if (src_on_device) {
         scatter_columns_kernel<<<grid_for(d->n * ncols, 256, d->sm_count), 256>>>(d->X, d->n, d->ld, col0, ncols, src, src_ld);
         CU_TRY(cudaGetLastError());
@@ -384,6 +471,7 @@ extern "C" int anml_design_validate_columns(const anml_design* d, int col0, int 
     for (int c = 0; c < ncols; ++c) flags_out[c] = 0;
     if (d->n == 0) return ANML_OK;
     CU_TRY(cudaSetDevice(d->device));
+    TRY(design_materialize(const_cast<anml_design*>(d)));
     int* flags = nullptr;
     CU_TRY(cudaMalloc(&flags, (size_t)ncols * sizeof(int)));
     cudaError_t e = cudaMemset(flags, 0, (size_t)ncols * sizeof(int));
@@ -579,6 +667,21 @@ extern "C" int anml_design_set_spline(anml_design* d, int col0, const double* x,
     const int nb = n_knots - 1 + degree;
     if (col0 < 0 || col0 + nb > d->p) return fail(ANML_EINVAL, "anml_design_set_spline: %d basis columns at %d do not fit a %d-column design", nb, col0, d->p);
     CU_TRY(cudaSetDevice(d->device));
+    if (d->deferred && !d->X && x_on_device && !interval_out) {
+        // record the block; it is evaluated if and when the dense matrix is needed (design_materialize)
+        if (n_knots < 2 || n_knots > SPLINE_MAX_KNOTS) return fail(ANML_EINVAL, "spline needs between 2 and %d knots, got %d", SPLINE_MAX_KNOTS, n_knots);
+        if (degree < 0 || degree > SPLINE_MAX_DEGREE) return fail(ANML_EUNSUPPORTED, "spline degree must be in [0, %d], got %d", SPLINE_MAX_DEGREE, degree);
+        if (order < 0) return fail(ANML_EINVAL, "spline derivative order must be non-negative");
+        for (int i = 1; i < n_knots; ++i)
+            if (!(knots[i] >= knots[i - 1])) return fail(ANML_EINVAL, "spline knots must be sorted ascending");
+        if (!(knots[n_knots - 1] > knots[0])) return fail(ANML_EINVAL, "spline knots must span a non-empty interval");
+        anml_design::PendingSpline ps;
+        ps.col0 = col0; ps.x_dev = x; ps.knots.assign(knots, knots + n_knots);
+        ps.degree = degree; ps.ldegree = ldegree; ps.rdegree = rdegree; ps.order = order;
+        d->pending.push_back(ps);
+        return ANML_OK;
+    }
+    TRY(design_materialize(d));
     double* x_tmp = nullptr;
     int32_t* idx_dev = nullptr;
     const size_t nn = (size_t)(d->n > 0 ? d->n : 1);
@@ -613,6 +716,7 @@ extern "C" int anml_design_download(const anml_design* d, double* host_out, int6
     if (!d || !host_out || out_ld < d->p) return fail(ANML_EINVAL, "anml_design_download: bad arguments");
     if (d->n == 0) return ANML_OK;
     CU_TRY(cudaSetDevice(d->device));
+    TRY(design_materialize(const_cast<anml_design*>(d)));
     CU_TRY(cudaMemcpy2D(host_out, (size_t)out_ld * sizeof(double), d->X, (size_t)d->ld * sizeof(double), (size_t)d->p * sizeof(double),
                         (size_t)d->n, cudaMemcpyDeviceToHost));
     return ANML_OK;
@@ -664,6 +768,7 @@ extern "C" int anml_design_params(const anml_design* d, const double* beta_host,
     if (link < 0 || link > 4) return fail(ANML_EINVAL, "unknown link %d", link);
     if (d->n == 0) return ANML_OK;
     CU_TRY(cudaSetDevice(d->device));
+    TRY(design_materialize(const_cast<anml_design*>(d)));
     const long long n = d->n;
     const int p = d->p;
     long long out_elems = n;
@@ -751,14 +856,13 @@ static void free_eval_buffers(anml_model* m) {
     if (m->d_packed) cudaFree(m->d_packed);
     if (m->h_packed) cudaFreeHost(m->h_packed);
     if (m->d_partials) cudaFree(m->d_partials);
-    if (m->d_reduced) cudaFree(m->d_reduced);
     if (m->d_status) cudaFree(m->d_status);
     if (m->d_wide) cudaFree(m->d_wide);
     for (double*& v : m->vec) {
         if (v) cudaFree(v);
         v = nullptr;
     }
-    m->d_beta = m->h_beta = m->d_packed = m->h_packed = m->d_partials = m->d_reduced = m->d_wide = nullptr;
+    m->d_beta = m->h_beta = m->d_packed = m->h_packed = m->d_partials = m->d_wide = nullptr;
     m->d_status = nullptr;
     m->wide_len = 0;
     m->ready = false;
@@ -770,13 +874,27 @@ static void free_banded(anml_model* m) {
     for (double* q : bufs)
         if (q) cudaFree(q);
     if (b.perm) cudaFree(b.perm);
+    if (b.seg) cudaFree(b.seg);
     b = anml_model::Banded();
+}
+
+// Nothing of this model is in flight any more: the last evaluation (possibly on a caller's stream,
+// anml_model_eval_async) and the model's own stream have drained.  Setters call it before they touch
+// buffers an evaluation reads.
+static int model_quiesce(anml_model* m) {
+    if (m->eval_pending && m->eval_done) {
+        CU_TRY(cudaEventSynchronize(m->eval_done));
+        m->eval_pending = false;
+    }
+    if (m->stream) CU_TRY(cudaStreamSynchronize(m->stream));
+    return ANML_OK;
 }
 
 extern "C" int anml_model_destroy(anml_model* m) {
     if (!m) return ANML_OK;
     cudaSetDevice(m->device);
-    if (m->stream) cudaStreamSynchronize(m->stream);
+    (void)model_quiesce(m);
+    if (m->eval_done) cudaEventDestroy(m->eval_done);
     free_eval_buffers(m);
     free_banded(m);
     for (int k = 0; k < 2; ++k) free_prior(m->par[k].prior);
@@ -800,7 +918,7 @@ extern "C" int anml_model_set_param(anml_model* m, int k, const anml_design* des
     if (design->n != m->n) return fail(ANML_EINVAL, "design has %lld rows, model has %lld", design->n, m->n);
     if (design->device != m->device) return fail(ANML_EINVAL, "design lives on device %d, model on %d", design->device, m->device);
     CU_TRY(cudaSetDevice(m->device));
-    if (m->stream) CU_TRY(cudaStreamSynchronize(m->stream));
+    TRY(model_quiesce(m));
     if (m->par[k].design && m->par[k].design->p != design->p) {
         free_prior(m->par[k].prior);
         free_eval_buffers(m);
@@ -814,7 +932,7 @@ extern "C" int anml_model_set_param(anml_model* m, int k, const anml_design* des
 
 static int set_row_vector(anml_model* m, const double* src, int on_device, const double** view, double** owned) {
     CU_TRY(cudaSetDevice(m->device));
-    if (m->stream) CU_TRY(cudaStreamSynchronize(m->stream));
+    TRY(model_quiesce(m));
     m->banded.gathered = false;  // the sorted copies are stale
     if (*owned) {
         CU_TRY(cudaFree(*owned));
@@ -860,10 +978,8 @@ extern "C" int anml_model_set_gaussian_prior(anml_model* m, int k, const double*
     if (k < 0 || k >= m->K || !m->par[k].design) return fail(ANML_ESTATE, "set the design of parameter %d before its prior", k);
     if (n_lin < 0 || (n_lin > 0 && (!lin_mat || !lin_mean || !lin_sd))) return fail(ANML_EINVAL, "linear prior arrays missing");
     CU_TRY(cudaSetDevice(m->device));
-    if (m->stream) CU_TRY(cudaStreamSynchronize(m->stream));
     const int p = m->par[k].design->p;
-    PriorStore& s = m->par[k].prior;
-    free_prior(s);
+    // validate and build everything on the host first: a rejected call leaves the installed prior in place
     std::vector<double> mu(p, 0.0), iv(p, 0.0);
     for (int j = 0; j < p; ++j) {
         if (mean) mu[j] = mean[j];
@@ -888,14 +1004,22 @@ extern "C" int anml_model_set_gaussian_prior(anml_model* m, int k, const double*
         }
     for (int a = 0; a < p && n_lin > 0; ++a)  // mirror the lower triangle: exactly symmetric
         for (int b = 0; b < a; ++b) lh[(size_t)b * p + a] = lh[(size_t)a * p + b];
-    TRY(upload_vec(&s.mean, mu));
-    TRY(upload_vec(&s.inv_var, iv));
-    TRY(upload_vec(&s.lin_mat, lmat));
-    TRY(upload_vec(&s.lin_mean, lmean));
-    TRY(upload_vec(&s.lin_inv_var, liv));
-    TRY(upload_vec(&s.lin_hess, lh));
-    s.m = n_lin;
-    s.set = true;
+    PriorStore fresh;
+    int rc = upload_vec(&fresh.mean, mu);
+    if (rc == ANML_OK) rc = upload_vec(&fresh.inv_var, iv);
+    if (rc == ANML_OK) rc = upload_vec(&fresh.lin_mat, lmat);
+    if (rc == ANML_OK) rc = upload_vec(&fresh.lin_mean, lmean);
+    if (rc == ANML_OK) rc = upload_vec(&fresh.lin_inv_var, liv);
+    if (rc == ANML_OK) rc = upload_vec(&fresh.lin_hess, lh);
+    if (rc != ANML_OK) {
+        free_prior(fresh);
+        return rc;
+    }
+    fresh.m = n_lin;
+    fresh.set = true;
+    TRY(model_quiesce(m));  // the old arrays may still be read by an evaluation in flight
+    free_prior(m->par[k].prior);
+    m->par[k].prior = fresh;
     return ANML_OK;
 }
 
@@ -931,8 +1055,7 @@ static int fused_el(int nb16, bool hess) {
     return ((hess ? 2 * nt : 0) + nb8 + 1) * 32;
 }
 
-static int ensure_buffers(anml_model* m) {
-    if (m->ready) return ANML_OK;
+static int ensure_buffers_alloc(anml_model* m) {
     int P = 0;
     TRY(anml_model_num_coefs(m, &P));
     if (!m->obs) return fail(ANML_ESTATE, "observations not set");
@@ -959,9 +1082,22 @@ static int ensure_buffers(anml_model* m) {
     if ((long long)m->sm_count * 8 > plen) plen = (long long)m->sm_count * 8;
     m->partials_len = plen;
     CU_TRY(cudaMalloc(&m->d_partials, (size_t)plen * sizeof(double)));
-    CU_TRY(cudaMalloc(&m->d_reduced, (size_t)fused_el(4, true) * sizeof(double)));
     CU_TRY(cudaMalloc(&m->d_status, sizeof(int)));
+    CU_TRY(cudaMemset(m->d_status, 0, sizeof(int)));  // re-armed by the last launch of every evaluation
     if (!m->beta_copied) CU_TRY(cudaEventCreateWithFlags(&m->beta_copied, cudaEventDisableTiming));
+    if (!m->eval_done) CU_TRY(cudaEventCreateWithFlags(&m->eval_done, cudaEventDisableTiming));
+    return ANML_OK;
+}
+
+static int ensure_buffers(anml_model* m) {
+    if (m->ready) return ANML_OK;
+    const int rc = ensure_buffers_alloc(m);
+    if (rc != ANML_OK) {
+        const std::string msg = g_err;
+        free_eval_buffers(m);  // no half-allocated set survives a failure (a retry would leak it)
+        g_err = msg;
+        return rc;
+    }
     m->ready = true;
     return ANML_OK;
 }
@@ -1045,9 +1181,59 @@ static bool weights_positive(int family, int link, bool fast) {
            (family == ANML_FAMILY_POISSON && link == ANML_LINK_EXP);
 }
 
-// Two-parameter model over ONE design with p <= 64: a single streaming pass computes both
-// linear predictors, the row terms (r0, r1, w00, w01, w11 -> device vectors) and the objective.
-static int run_dual_terms(anml_model* m, cudaStream_t st) {
+static PriorDev prior_dev(const anml_model* m, int k) {
+    PriorDev pd;
+    memset(&pd, 0, sizeof(pd));
+    const PriorStore& s = m->par[k].prior;
+    if (!m->prior_enabled || !s.set) return pd;
+    pd.on = 1; pd.p = m->par[k].design->p; pd.off = m->par[k].off; pd.m = s.m;
+    pd.mean = s.mean; pd.inv_var = s.inv_var; pd.lin_mat = s.lin_mat; pd.lin_mean = s.lin_mean;
+    pd.lin_inv_var = s.lin_inv_var; pd.lin_hess = s.lin_hess;
+    return pd;
+}
+
+// What the one-launch epilogue (finish.cuh) does with the partial record of a fused block
+struct FinishPlan {
+    int row_off = 0, col_off = 0;
+    bool write_grad = true;
+    int obj_mode = 1;        // 0 leave, 1 write (+ prior objectives), 2 accumulate
+    bool write_flag = false; // last launch of the evaluation: publish the domain flag
+    int prior_k = -1;        // parameter whose prior gradient / Hessian terms ride on this block (-1: none)
+    bool prior_obj = false;  // add every parameter's prior objective (with obj_mode 1)
+};
+
+static int launch_finish(anml_model* m, int grid, int nb16, bool hess, int p, const FinishPlan& plan, double* packed, cudaStream_t st) {
+    FinishArgs f;
+    memset(&f, 0, sizeof(f));
+    f.partials = m->d_partials; f.ncta = grid; f.el = fused_el(nb16, hess);
+    f.nb16 = nb16; f.hess = hess ? 1 : 0; f.p = p;
+    f.packed = packed; f.P_total = m->P; f.row_off = plan.row_off; f.col_off = plan.col_off;
+    f.write_grad = plan.write_grad ? 1 : 0; f.obj_mode = plan.obj_mode; f.write_flag = plan.write_flag ? 1 : 0;
+    f.beta = m->d_beta; f.status = m->d_status;
+    int max_m = 0;
+    if (plan.prior_k >= 0) {
+        f.prior = prior_dev(m, plan.prior_k);
+        if (f.prior.on) max_m = f.prior.m;
+    }
+    if (plan.prior_obj && plan.obj_mode == 1) {
+        for (int k = 0; k < m->K; ++k) {
+            f.prior_obj[k] = prior_dev(m, k);
+            if (f.prior_obj[k].on && f.prior_obj[k].m > max_m) max_m = f.prior_obj[k].m;
+        }
+        f.n_prior_obj = m->K;
+    }
+    const size_t smem = (size_t)(max_m > 0 ? max_m : 1) * sizeof(double);
+    if (smem > 40 * 1024) return fail(ANML_EUNSUPPORTED, "more than 5120 linear prior rows on one parameter");
+    finish_fused_kernel<<<f.el / 32, 128, smem, st>>>(f);
+    CU_TRY(cudaGetLastError());
+    m->all_launches += 1;
+    return ANML_OK;
+}
+
+// Two-parameter model over ONE design with p <= 64, gradient-only evaluation: a single streaming pass
+// computes both linear predictors, the row terms (r0, r1, ... -> device vectors) and the objective.
+// (With the Hessian wanted, fused_hess_kernel MODE 3 does this inside the first Hessian launch.)
+static int run_dual_terms(anml_model* m, double* packed, cudaStream_t st) {
     const anml_design* d = m->par[0].design;
     const int nb16 = (d->p + 15) / 16;
     const long long nblk = (d->n + 31) / 32;
@@ -1069,22 +1255,21 @@ static int run_dual_terms(anml_model* m, cudaStream_t st) {
         default: rc = launch_fused_t<4, false, 2>(d, a, grid, st); break;
     }
     TRY(rc);
-    const int el = fused_el(nb16, false);
-    reduce_partials_kernel<<<(el + 127) / 128, 128, 0, st>>>(m->d_partials, grid, el, m->d_reduced);
-    CU_TRY(cudaGetLastError());
-    assemble_kernel<<<1, 256, 0, st>>>(m->d_reduced, nb16, 0, d->p, m->d_packed, m->P, 0, 0, 0, 0);  // objective only
-    CU_TRY(cudaGetLastError());
-    m->all_launches += 3;
-    return ANML_OK;
+    m->all_launches += 1;
+    FinishPlan plan;
+    plan.write_grad = false; plan.obj_mode = 1; plan.prior_obj = true;  // objective (+ prior objectives) only
+    return launch_finish(m, grid, nb16, false, d->p, plan, packed, st);
 }
 
-// fused kernel + partial reduction + layout undo for one parameter block
-static int run_fused_block(anml_model* m, const anml_design* d, FusedArgs a, bool hess, int mode, int row_off, int col_off,
-                           bool write_grad, bool add_obj, bool timed, cudaStream_t st) {
+// fused kernel + one-launch epilogue for one parameter block.
+// mode 0: terms from X, beta, obs; 1: (r, w) from a.rvec / a.wvec; 3: dual-predictor terms + block (0, 0)
+static int run_fused_block(anml_model* m, const anml_design* d, FusedArgs a, bool hess, int mode, const FinishPlan& plan, double* packed,
+                           bool timed, cudaStream_t st) {
     const int nb16 = (d->p + 15) / 16;
     if (nb16 > 4) return fail(ANML_EUNSUPPORTED, "fused path handles at most 64 columns");
     const long long nblk = (d->n + 31) / 32;
-    const bool specialised = hess && !m->no_specialise;
+    const bool specialised = hess && !m->no_specialise && mode != 2;
+    if (mode == 3 && !specialised) return fail(ANML_ESTATE, "dual-predictor mode needs the warp-specialised Hessian kernel");
     int grid = (int)((nblk + (specialised ? 3 : 7)) / (specialised ? 4 : 8));
     if (grid > m->sm_count) grid = m->sm_count;
     if (grid < 1) grid = 1;
@@ -1102,7 +1287,8 @@ static int run_fused_block(anml_model* m, const anml_design* d, FusedArgs a, boo
         const bool sgn = !weights_positive(a.family, a.link, a.fast != 0) || m->force_signed;
 #define HESS_CASE(NB)                                                                              \
     case NB:                                                                                       \
-        if (mode == 1) rc = launch_hess_t<NB, 2, true, 1>(d, a, grid, st);                         \
+        if (mode == 3) rc = launch_hess_t<NB, 2, true, 3>(d, a, grid, st);                         \
+        else if (mode == 1) rc = launch_hess_t<NB, 2, true, 1>(d, a, grid, st);                    \
         else rc = sgn ? launch_hess_t<NB, 2, true, 0>(d, a, grid, st) : launch_hess_t<NB, 2, false, 0>(d, a, grid, st); \
         break;
         switch (nb16) {
@@ -1122,18 +1308,14 @@ static int run_fused_block(anml_model* m, const anml_design* d, FusedArgs a, boo
 #undef FUSED_CASE
     TRY(rc);
     if (ep) CU_TRY(cudaEventRecord(ep->b, st));
-    const int el = fused_el(nb16, hess);
-    reduce_partials_kernel<<<(el + 127) / 128, 128, 0, st>>>(m->d_partials, grid, el, m->d_reduced);
-    CU_TRY(cudaGetLastError());
-    assemble_kernel<<<1, 256, 0, st>>>(m->d_reduced, nb16, hess ? 1 : 0, d->p, m->d_packed, m->P, row_off, col_off,
-                                       write_grad ? 1 : 0, add_obj ? 1 : 0);
-    CU_TRY(cudaGetLastError());
     m->main_launches += 1;
-    m->all_launches += 3;
-    return ANML_OK;
+    m->all_launches += 1;
+    return launch_finish(m, grid, nb16, hess, d->p, plan, packed, st);
 }
 
-static int run_priors(anml_model* m, int want, cudaStream_t st) {
+// Gaussian prior terms as a separate launch: only the paths whose epilogue is not the fused one
+// (designs wider than 64 columns, two different designs) still use it.
+static int run_priors(anml_model* m, int want, double* packed, cudaStream_t st) {
     if (!m->prior_enabled) return ANML_OK;
     for (int k = 0; k < m->K; ++k) {
         const PriorStore& s = m->par[k].prior;
@@ -1141,7 +1323,7 @@ static int run_priors(anml_model* m, int want, cudaStream_t st) {
         PriorArgs a;
         a.p = m->par[k].design->p; a.off = m->par[k].off; a.P_total = m->P; a.m = s.m; a.want = want;
         a.beta = m->d_beta; a.mean = s.mean; a.inv_var = s.inv_var; a.lin_mat = s.lin_mat; a.lin_mean = s.lin_mean;
-        a.lin_inv_var = s.lin_inv_var; a.lin_hess = s.lin_hess; a.packed = m->d_packed;
+        a.lin_inv_var = s.lin_inv_var; a.lin_hess = s.lin_hess; a.packed = packed;
         const size_t smem = (size_t)(s.m > 0 ? s.m : 1) * sizeof(double);
         if (smem > 48 * 1024) return fail(ANML_EUNSUPPORTED, "more than 6144 linear prior rows on one parameter");
         add_priors_kernel<<<1, 256, smem, st>>>(a);
@@ -1151,13 +1333,12 @@ static int run_priors(anml_model* m, int want, cudaStream_t st) {
     return ANML_OK;
 }
 
-static int eval_general(anml_model* m, int want, cudaStream_t st);
-static EventPair* next_events(anml_model* m);
+static int eval_general(anml_model* m, int want, double* packed, cudaStream_t st);
 
 // H block (row_off, col_off) = Xa^T diag(w) Xb for designs wider than 64 columns
 // or two different designs (wide_hessian.cuh).
 static int run_wide_hessian(anml_model* m, const anml_design* da, const anml_design* db, const double* w, int row_off, int col_off,
-                            cudaStream_t st) {
+                            double* packed, cudaStream_t st) {
     const int nba = (da->p + 127) / 128, nbb = (db->p + 63) / 64;  // 128-column blocks of Xa, 64-column blocks of Xb
     const bool symmetric = (da == db) && (row_off == col_off);
     // symmetric: row bi of the block grid holds the 2*bi+2 blocks that touch or lie below the diagonal
@@ -1207,7 +1388,7 @@ static int run_wide_hessian(anml_model* m, const anml_design* da, const anml_des
     if (ep) CU_TRY(cudaEventRecord(ep->b, st));
     const long long total = (long long)npairs * WIDE_TILE_ELEMS;
     wide_reduce_kernel<<<grid_for(total, 256, m->sm_count, 8), 256, 0, st>>>(m->d_wide, (int)S, npairs, nbb, symmetric ? 1 : 0, da->p, db->p,
-                                                                            m->d_packed + 1 + m->P, m->P, row_off, col_off);
+                                                                            packed + 1 + m->P, m->P, row_off, col_off);
     CU_TRY(cudaGetLastError());
     m->main_launches += 1;
     m->all_launches += 2;
@@ -1217,21 +1398,26 @@ static int run_wide_hessian(anml_model* m, const anml_design* da, const anml_des
 // ----------------------------------------------------------------------------
 // banded spline evaluator (spline_eval.cuh)
 // ----------------------------------------------------------------------------
-constexpr int BANDED_CTAS_PER_SM = 2;  // 256-thread CTAs of 92 registers: two fit, and the row loop is latency-bound
+constexpr int BANDED_CTAS_PER_SM = 6;  // 2-3 resident CTAs per SM; a few slices per slot even out the tail
 
+// per-row vector gathered into the sorted order; two spare (zero) doubles so that the 16-byte loads of the
+// last row pair stay inside the allocation
 static int gather_sorted(anml_model* m, const double* src, double** dst, cudaStream_t st) {
     if (!src) {
         if (*dst) CU_TRY(cudaFree(*dst));
         *dst = nullptr;
         return ANML_OK;
     }
-    if (!*dst) CU_TRY(cudaMalloc(dst, (size_t)m->n * sizeof(double)));
+    if (!*dst) {
+        CU_TRY(cudaMalloc(dst, (size_t)(m->n + 2) * sizeof(double)));
+        CU_TRY(cudaMemsetAsync(*dst + m->n, 0, 2 * sizeof(double), st));
+    }
     gather_rows_kernel<<<grid_for(m->n, 256, m->sm_count, 8), 256, 0, st>>>(*dst, src, m->banded.perm, m->n);
     CU_TRY(cudaGetLastError());
     return ANML_OK;
 }
 
-static int eval_banded(anml_model* m, int want, cudaStream_t st) {
+static int eval_banded(anml_model* m, int want, double* packed, cudaStream_t st) {
     anml_model::Banded& b = m->banded;
     if (!m->obs) return fail(ANML_ESTATE, "observations not set");
     if (!b.gathered) {
@@ -1244,23 +1430,19 @@ static int eval_banded(anml_model* m, int want, cudaStream_t st) {
     const bool hess = (want & ANML_WANT_HESS) != 0;
     BandedArgs a;
     a.xs = b.xs; a.obs = b.obs_s; a.se = b.se_s; a.offset = b.off_s; a.weights = b.w_s;
-    a.n = m->n; a.t = b.t_dev; a.coef = b.coef; a.nk = b.nk; a.beta = m->d_beta;
-    const size_t coef_bytes = (size_t)(b.nk - 1) * (b.degree + 1) * (b.degree + 1) * sizeof(double);
-    a.coef_in_smem = coef_bytes <= 24 * 1024 ? 1 : 0;
-    a.family = m->family; a.link = m->par[0].link; a.fast = m->no_fast ? 0 : 1; a.want_hess = hess ? 1 : 0;
-    a.rows_per_warp = b.rows_per_warp; a.partials = b.partials; a.status = m->d_status;
-    CU_TRY(cudaMemsetAsync(b.partials, 0, (size_t)b.nwarps * b.rec * sizeof(double), st));
-    const int grid = (int)(b.nwarps / 8);
-    const size_t smem = (size_t)(((b.nk + 2 * b.degree + 1) & ~1) + ((b.nb + 1) & ~1)) * sizeof(double) + (a.coef_in_smem ? coef_bytes : 0);
+    a.n = m->n; a.knots = b.t_dev + b.degree; a.coef = b.coef; a.seg = b.seg; a.nk = b.nk; a.beta = m->d_beta;
+    a.family = m->family; a.link = m->par[0].link; a.fast = m->no_fast ? 0 : 1;
+    a.rows_per_cta = b.rows_per_cta; a.partials = b.partials; a.status = m->d_status;
     EventPair* ep = next_events(m);
     if (ep) CU_TRY(cudaEventRecord(ep->a, st));
-#define BANDED_LAUNCH(D)                                                                          \
-    if (a.coef_in_smem) {                                                                         \
-        if (hess) spline_banded_eval_kernel<D, true, true><<<grid, 256, smem, st>>>(a);           \
-        else spline_banded_eval_kernel<D, true, false><<<grid, 256, smem, st>>>(a);               \
-    } else {                                                                                      \
-        if (hess) spline_banded_eval_kernel<D, false, true><<<grid, 256, smem, st>>>(a);          \
-        else spline_banded_eval_kernel<D, false, false><<<grid, 256, smem, st>>>(a);              \
+    const bool extras = a.se || a.offset || a.weights;
+#define BANDED_LAUNCH(D)                                                                      \
+    if (extras) {                                                                             \
+        if (hess) spline_banded_eval_kernel<D, true, true><<<b.grid, 256, 0, st>>>(a);        \
+        else spline_banded_eval_kernel<D, false, true><<<b.grid, 256, 0, st>>>(a);            \
+    } else {                                                                                  \
+        if (hess) spline_banded_eval_kernel<D, true, false><<<b.grid, 256, 0, st>>>(a);       \
+        else spline_banded_eval_kernel<D, false, false><<<b.grid, 256, 0, st>>>(a);           \
     }
     switch (b.degree) {
         case 1: BANDED_LAUNCH(1) break;
@@ -1270,9 +1452,14 @@ static int eval_banded(anml_model* m, int want, cudaStream_t st) {
 #undef BANDED_LAUNCH
     CU_TRY(cudaGetLastError());
     if (ep) CU_TRY(cudaEventRecord(ep->b, st));
-    banded_reduce_kernel<<<(b.rec + 31) / 32, dim3(32, 32), 0, st>>>(b.partials, b.nwarps, b.rec, b.reduced);
+    banded_reduce_kernel<<<(b.rec + 31) / 32, dim3(32, 32), 0, st>>>(b.partials, b.grid, b.rec, b.reduced);
     CU_TRY(cudaGetLastError());
-    banded_assemble_kernel<<<(1 + m->P + (hess ? m->P * m->P : 0) + 255) / 256, 256, 0, st>>>(b.reduced, b.nk - 1, b.degree, hess ? 1 : 0, m->d_packed, m->P);
+    BandedFinishArgs f;
+    f.reduced = b.reduced; f.coef = b.coef; f.nint = b.nk - 1; f.deg = b.degree; f.hess = hess ? 1 : 0; f.P = m->P;
+    f.packed = packed; f.beta = m->d_beta; f.prior = prior_dev(m, 0); f.status = m->d_status;
+    const size_t smem = (size_t)(f.prior.on && f.prior.m > 0 ? f.prior.m : 1) * sizeof(double);
+    if (smem > 40 * 1024) return fail(ANML_EUNSUPPORTED, "more than 5120 linear prior rows on one parameter");
+    banded_finish_kernel<<<(1 + m->P + (hess ? m->P * m->P : 0) + 255) / 256, 256, smem, st>>>(f);
     CU_TRY(cudaGetLastError());
     m->main_launches += 1;
     m->all_launches += 3;
@@ -1290,7 +1477,7 @@ extern "C" int anml_model_enable_banded_spline(anml_model* m, const double* x, i
     for (int i = 1; i < n_knots; ++i)
         if (!(knots[i] >= knots[i - 1])) return fail(ANML_EINVAL, "spline knots must be sorted ascending");
     CU_TRY(cudaSetDevice(m->device));
-    if (m->stream) CU_TRY(cudaStreamSynchronize(m->stream));
+    TRY(model_quiesce(m));
     free_banded(m);
     anml_model::Banded& b = m->banded;
     const long long n = m->n;
@@ -1300,13 +1487,15 @@ extern "C" int anml_model_enable_banded_spline(anml_model* m, const double* x, i
     int32_t* iota = nullptr;
     void* temp = nullptr;
     size_t temp_bytes = 0;
-    cudaError_t e = cudaMalloc(&b.xs, (size_t)n * sizeof(double));
+    cudaError_t e = cudaMalloc(&b.xs, (size_t)(n + 2) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemset(b.xs + n, 0, 2 * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&b.perm, (size_t)n * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&iota, (size_t)n * sizeof(int32_t));
     if (e == cudaSuccess) {
         iota_kernel<<<grid_for(n, 256, m->sm_count, 8), 256>>>(iota, n);
         e = cudaGetLastError();
     }
+    // one-off at attach; CUB's radix sort is library code and off the evaluation path
     if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, xd, b.xs, iota, b.perm, (int)n);
     if (e == cudaSuccess) e = cudaMalloc(&temp, temp_bytes ? temp_bytes : 16);
     if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, xd, b.xs, iota, b.perm, (int)n);
@@ -1333,15 +1522,22 @@ extern "C" int anml_model_enable_banded_spline(anml_model* m, const double* x, i
     for (int i = 0; i < degree; ++i) t[i] = knots[0];
     for (int i = 0; i < n_knots; ++i) t[degree + i] = knots[i];
     for (int i = 0; i < degree; ++i) t[degree + n_knots + i] = knots[n_knots - 1];
-    const int slots = (degree + 1) + (degree + 1) * (degree + 2) / 2;
-    b.nk = n_knots; b.degree = degree; b.nb = nb; b.rec = (n_knots - 1) * slots + 1;
-    b.nwarps = (long long)m->sm_count * 8 * BANDED_CTAS_PER_SM;
-    long long rpw = (n + b.nwarps - 1) / b.nwarps;
-    b.rows_per_warp = (rpw + 31) / 32 * 32;
+    const int nm = (degree + 1) + (2 * degree + 1);  // gradient + Hessian power moments per interval
+    b.nk = n_knots; b.degree = degree; b.nb = nb; b.rec = (n_knots - 1) * nm + 1;
+    // equal, contiguous, even-sized row slices; never more CTAs than 512-row slices
+    long long grid = (long long)m->sm_count * BANDED_CTAS_PER_SM;
+    const long long max_grid = (n + 511) / 512;
+    if (grid > max_grid) grid = max_grid;
+    if (grid < 1) grid = 1;
+    long long rpc = (n + grid - 1) / grid;
+    rpc += rpc & 1;
+    b.rows_per_cta = rpc;
+    b.grid = (int)((n + rpc - 1) / rpc);
     e = cudaMalloc(&b.t_dev, nt * sizeof(double));
     if (e == cudaSuccess) e = cudaMemcpy(b.t_dev, t.data(), nt * sizeof(double), cudaMemcpyHostToDevice);
     const int ncoef = (n_knots - 1) * (degree + 1) * (degree + 1);
     if (e == cudaSuccess) e = cudaMalloc(&b.coef, (size_t)ncoef * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&b.seg, (size_t)n_knots * sizeof(long long));
     if (e == cudaSuccess) {
         const int work = (n_knots - 1) * (degree + 1);
         switch (degree) {
@@ -1349,10 +1545,11 @@ extern "C" int anml_model_enable_banded_spline(anml_model* m, const double* x, i
             case 2: banded_coeff_kernel<2><<<(work + 127) / 128, 128>>>(b.t_dev, n_knots, b.coef); break;
             default: banded_coeff_kernel<3><<<(work + 127) / 128, 128>>>(b.t_dev, n_knots, b.coef); break;
         }
+        banded_segments_kernel<<<(n_knots + 127) / 128, 128>>>(b.xs, n, b.t_dev + degree, n_knots, b.seg);
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
     }
-    if (e == cudaSuccess) e = cudaMalloc(&b.partials, (size_t)b.nwarps * b.rec * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&b.partials, (size_t)b.grid * b.rec * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&b.reduced, (size_t)b.rec * sizeof(double));
     if (e != cudaSuccess) {
         const int code = (e == cudaErrorMemoryAllocation) ? ANML_ENOMEM : ANML_ECUDA;
@@ -1365,11 +1562,17 @@ extern "C" int anml_model_enable_banded_spline(anml_model* m, const double* x, i
     return ANML_OK;
 }
 
-static int eval_on_stream(anml_model* m, const double* x_host, int want, cudaStream_t st) {
+static int eval_on_stream(anml_model* m, const double* x_host, int want, double* packed, cudaStream_t st) {
     TRY(ensure_buffers(m));
     for (int k = 0; k < m->K; ++k)
         if (m->par[k].design->n != m->n) return fail(ANML_ESTATE, "design of parameter %d changed shape", k);
+    if (!packed) packed = m->d_packed;
     const bool hess = (want & ANML_WANT_HESS) != 0;
+    const bool banded = m->banded.enabled && !m->force_generic;
+    if (!banded)  // a deferred (spline) design is built the first time something streams it
+        for (int k = 0; k < m->K; ++k) TRY(design_materialize(const_cast<anml_design*>(m->par[k].design)));
+    // work of the previous evaluation may still be running on another stream (anml_model_eval_async)
+    if (m->eval_pending && m->last_stream != st) CU_TRY(cudaStreamWaitEvent(st, m->eval_done, 0));
     // stage beta: [x (P) | zero-padded copy per parameter]
     if (m->beta_pending) {
         CU_TRY(cudaEventSynchronize(m->beta_copied));
@@ -1381,30 +1584,34 @@ static int eval_on_stream(anml_model* m, const double* x_host, int want, cudaStr
     CU_TRY(cudaMemcpyAsync(m->d_beta, m->h_beta, m->beta_len * sizeof(double), cudaMemcpyHostToDevice, st));
     CU_TRY(cudaEventRecord(m->beta_copied, st));
     m->beta_pending = true;
-    CU_TRY(cudaMemsetAsync(m->d_status, 0, sizeof(int), st));
+    // d_status is zero here: zeroed at allocation, and every evaluation's last launch re-arms it
 
     const anml_design* d0 = m->par[0].design;
-    if (m->banded.enabled && !m->force_generic) {
-        TRY(eval_banded(m, want, st));
+    if (banded) {
+        TRY(eval_banded(m, want, packed, st));
     } else if (m->K == 1 && d0->p <= 64 && !m->force_generic) {
         FusedArgs a;
+        memset(&a, 0, sizeof(a));
         a.n = m->n; a.p = d0->p; a.link = m->par[0].link; a.family = m->family; a.fast = m->no_fast ? 0 : 1;
         a.beta = m->d_beta + m->par[0].pad_off; a.obs = m->obs; a.se = m->se; a.offset = m->par[0].offset; a.weights = m->weights;
-        a.rvec = nullptr; a.wvec = nullptr; a.partials = nullptr; a.status = nullptr;
-        TRY(run_fused_block(m, d0, a, hess, 0, 0, 0, true, false, true, st));
+        FinishPlan plan;
+        plan.write_flag = true; plan.prior_k = 0; plan.prior_obj = true;
+        TRY(run_fused_block(m, d0, a, hess, 0, plan, packed, true, st));
     } else {
-        TRY(eval_general(m, want, st));
+        TRY(eval_general(m, want, packed, st));
     }
-    TRY(run_priors(m, want, st));
-    set_flag_kernel<<<1, 1, 0, st>>>(m->d_packed + 1 + m->P + (size_t)m->P * m->P, m->d_status);
-    CU_TRY(cudaGetLastError());
-    m->all_launches += 1;
+    CU_TRY(cudaEventRecord(m->eval_done, st));
+    m->eval_pending = true;
+    m->last_stream = st;
     return ANML_OK;
 }
 
-// General path: any K <= 2, any width.  linear predictors -> row terms ->
-// per-block gradient / Hessian kernels.
-static int eval_general(anml_model* m, int want, cudaStream_t st) {
+// General path: any K <= 2, any width.
+//   * two parameters over ONE design of at most 64 columns (BASELINE config #4): fused_hess MODE 3 (both
+//     predictors, row terms, objective, g0, H00) -> MODE 1 (r1, w11 -> g1, H11) -> MODE 1 (w01 -> H01):
+//     X is read three times, priors and the domain flag ride on the three one-launch epilogues;
+//   * otherwise linear predictors -> row terms -> per-block gradient / Hessian kernels.
+static int eval_general(anml_model* m, int want, double* packed, cudaStream_t st) {
     const bool hess = (want & ANML_WANT_HESS) != 0;
     const int K = m->K;
     for (int k = 0; k < K; ++k) {
@@ -1418,25 +1625,62 @@ static int eval_general(anml_model* m, int want, cudaStream_t st) {
     }
     const bool dual = (K == 2) && (m->par[0].design == m->par[1].design) && (m->par[0].design->p <= 64) && !m->force_generic;
     if (dual) {
-        TRY(run_dual_terms(m, st));
-    } else {
-        for (int k = 0; k < K; ++k) {
-            TRY(launch_linpred(m->par[k].design, m->d_beta + m->par[k].off, m->par[k].offset, 0, -1, m->vec[k], m->d_status, st));
-            m->all_launches += 1;
+        const anml_design* d = m->par[0].design;
+        const int off0 = m->par[0].off, off1 = m->par[1].off;
+        if (hess && !m->no_specialise) {
+            FusedArgs a;
+            memset(&a, 0, sizeof(a));
+            a.n = m->n; a.p = d->p; a.link = m->par[0].link; a.link1 = m->par[1].link; a.family = m->family;
+            a.beta = m->d_beta + m->par[0].pad_off; a.beta1 = m->d_beta + m->par[1].pad_off;
+            a.obs = m->obs; a.offset = m->par[0].offset; a.offset1 = m->par[1].offset; a.weights = m->weights;
+            a.out_r1 = m->vec[3]; a.out_w01 = m->vec[5]; a.out_w11 = m->vec[6];
+            FinishPlan p0;
+            p0.row_off = off0; p0.col_off = off0; p0.prior_k = 0; p0.prior_obj = true;
+            TRY(run_fused_block(m, d, a, true, 3, p0, packed, true, st));
+        } else {
+            TRY(run_dual_terms(m, packed, st));  // objective + (r0, r1, w00, w01, w11)
+            FusedArgs a;
+            memset(&a, 0, sizeof(a));
+            a.n = m->n; a.p = d->p; a.rvec = m->vec[2]; a.wvec = m->vec[4];
+            FinishPlan p0;
+            p0.row_off = off0; p0.col_off = off0; p0.prior_k = 0; p0.obj_mode = 0;
+            TRY(run_fused_block(m, d, a, hess, 1, p0, packed, true, st));
         }
-        RowTermsArgs ra;
-        ra.n = m->n; ra.family = m->family; ra.nparams = K; ra.link0 = m->par[0].link; ra.link1 = (K == 2) ? m->par[1].link : 0;
-        ra.fast = m->no_fast ? 0 : 1;
-        ra.y0 = m->vec[0]; ra.y1 = m->vec[1]; ra.obs = m->obs; ra.se = m->se; ra.weights = m->weights;
-        ra.r0 = m->vec[2]; ra.r1 = m->vec[3]; ra.w00 = m->vec[4]; ra.w01 = m->vec[5]; ra.w11 = m->vec[6];
-        ra.obj_partials = m->d_partials; ra.status = m->d_status;
-        const int rgrid = grid_for(m->n, 256, m->sm_count, 8);
-        rowterms_kernel<<<rgrid, 256, 0, st>>>(ra);
-        CU_TRY(cudaGetLastError());
-        sum_partials_kernel<<<1, 256, 0, st>>>(m->d_partials, rgrid, m->d_packed, 0);
-        CU_TRY(cudaGetLastError());
-        m->all_launches += 2;
+        {
+            FusedArgs a;
+            memset(&a, 0, sizeof(a));
+            a.n = m->n; a.p = d->p; a.rvec = m->vec[3]; a.wvec = m->vec[6];
+            FinishPlan p1;
+            p1.row_off = off1; p1.col_off = off1; p1.prior_k = 1; p1.obj_mode = 0; p1.write_flag = !hess;
+            TRY(run_fused_block(m, d, a, hess, 1, p1, packed, true, st));
+        }
+        if (hess) {
+            FusedArgs a;
+            memset(&a, 0, sizeof(a));
+            a.n = m->n; a.p = d->p; a.rvec = nullptr; a.wvec = m->vec[5];
+            FinishPlan px;
+            px.row_off = off0; px.col_off = off1; px.write_grad = false; px.obj_mode = 0; px.write_flag = true;
+            TRY(run_fused_block(m, d, a, true, 1, px, packed, true, st));
+        }
+        return ANML_OK;
     }
+
+    for (int k = 0; k < K; ++k) {
+        TRY(launch_linpred(m->par[k].design, m->d_beta + m->par[k].off, m->par[k].offset, 0, -1, m->vec[k], m->d_status, st));
+        m->all_launches += 1;
+    }
+    RowTermsArgs ra;
+    ra.n = m->n; ra.family = m->family; ra.nparams = K; ra.link0 = m->par[0].link; ra.link1 = (K == 2) ? m->par[1].link : 0;
+    ra.fast = m->no_fast ? 0 : 1;
+    ra.y0 = m->vec[0]; ra.y1 = m->vec[1]; ra.obs = m->obs; ra.se = m->se; ra.weights = m->weights;
+    ra.r0 = m->vec[2]; ra.r1 = m->vec[3]; ra.w00 = m->vec[4]; ra.w01 = m->vec[5]; ra.w11 = m->vec[6];
+    ra.obj_partials = m->d_partials; ra.status = m->d_status;
+    const int rgrid = grid_for(m->n, 256, m->sm_count, 8);
+    rowterms_kernel<<<rgrid, 256, 0, st>>>(ra);
+    CU_TRY(cudaGetLastError());
+    sum_partials_kernel<<<1, 256, 0, st>>>(m->d_partials, rgrid, packed, 0);
+    CU_TRY(cudaGetLastError());
+    m->all_launches += 2;
 
     for (int k = 0; k < K; ++k) {
         const anml_design* d = m->par[k].design;
@@ -1445,7 +1689,9 @@ static int eval_general(anml_model* m, int want, cudaStream_t st) {
             FusedArgs a;
             memset(&a, 0, sizeof(a));
             a.n = m->n; a.p = d->p; a.rvec = m->vec[2 + k]; a.wvec = wkk;
-            TRY(run_fused_block(m, d, a, hess, 1, m->par[k].off, m->par[k].off, true, true, true, st));
+            FinishPlan plan;  // priors are added by run_priors below on this path
+            plan.row_off = m->par[k].off; plan.col_off = m->par[k].off; plan.obj_mode = 0;
+            TRY(run_fused_block(m, d, a, hess, 1, plan, packed, true, st));
         } else {
             // gradient: streaming X^T r
             const int nchunks = (int)((d->ld + 63) / 64);
@@ -1455,10 +1701,10 @@ static int eval_general(anml_model* m, int want, cudaStream_t st) {
             if ((long long)grid * d->ld > m->partials_len) grid = (int)(m->partials_len / d->ld);
             xtr_kernel<<<dim3(grid, nchunks), 256, 0, st>>>(d->X, d->n, d->ld, m->vec[2 + k], m->d_partials);
             CU_TRY(cudaGetLastError());
-            column_sum_kernel<<<(d->p + 255) / 256, 256, 0, st>>>(m->d_partials, grid, d->ld, d->p, m->d_packed + 1 + m->par[k].off);
+            column_sum_kernel<<<(d->p + 255) / 256, 256, 0, st>>>(m->d_partials, grid, d->ld, d->p, packed + 1 + m->par[k].off);
             CU_TRY(cudaGetLastError());
             m->all_launches += 2;
-            if (hess) TRY(run_wide_hessian(m, d, d, wkk, m->par[k].off, m->par[k].off, st));
+            if (hess) TRY(run_wide_hessian(m, d, d, wkk, m->par[k].off, m->par[k].off, packed, st));
         }
     }
     if (K == 2 && hess) {
@@ -1467,12 +1713,18 @@ static int eval_general(anml_model* m, int want, cudaStream_t st) {
         if (da == db && da->p <= 64) {
             FusedArgs a;
             memset(&a, 0, sizeof(a));
-            a.n = m->n; a.p = da->p; a.rvec = m->vec[5]; a.wvec = m->vec[5];
-            TRY(run_fused_block(m, da, a, true, 1, m->par[0].off, m->par[1].off, false, true, true, st));
+            a.n = m->n; a.p = da->p; a.rvec = nullptr; a.wvec = m->vec[5];
+            FinishPlan plan;
+            plan.row_off = m->par[0].off; plan.col_off = m->par[1].off; plan.write_grad = false; plan.obj_mode = 0;
+            TRY(run_fused_block(m, da, a, true, 1, plan, packed, true, st));
         } else {
-            TRY(run_wide_hessian(m, da, db, m->vec[5], m->par[0].off, m->par[1].off, st));
+            TRY(run_wide_hessian(m, da, db, m->vec[5], m->par[0].off, m->par[1].off, packed, st));
         }
     }
+    TRY(run_priors(m, want, packed, st));
+    set_flag_kernel<<<1, 1, 0, st>>>(packed + 1 + m->P + (size_t)m->P * m->P, m->d_status);
+    CU_TRY(cudaGetLastError());
+    m->all_launches += 1;
     return ANML_OK;
 }
 
@@ -1480,12 +1732,8 @@ extern "C" int anml_model_eval_async(anml_model* m, const double* x_host, int wa
     if (!m || !x_host) return fail(ANML_EINVAL, "anml_model_eval_async: NULL argument");
     CU_TRY(cudaSetDevice(m->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
-    TRY(eval_on_stream(m, x_host, want, st));
-    if (packed_dev && packed_dev != m->d_packed) {
-        const size_t packed = (size_t)2 + m->P + (size_t)m->P * m->P;
-        CU_TRY(cudaMemcpyAsync(packed_dev, m->d_packed, packed * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    }
-    return ANML_OK;
+    // the epilogue kernels write the packed record straight into the caller's buffer
+    return eval_on_stream(m, x_host, want, packed_dev, st);
 }
 
 extern "C" int anml_model_eval(anml_model* m, const double* x_host, int want, double* obj, double* grad, double* hess) {
@@ -1494,7 +1742,7 @@ extern "C" int anml_model_eval(anml_model* m, const double* x_host, int want, do
         return fail(ANML_EINVAL, "anml_model_eval: output buffer missing for a requested quantity");
     CU_TRY(cudaSetDevice(m->device));
     // the gradient is always produced (it rides on the same pass); the Hessian only on request
-    TRY(eval_on_stream(m, x_host, want | ANML_WANT_OBJ | ANML_WANT_GRAD, m->stream));
+    TRY(eval_on_stream(m, x_host, want | ANML_WANT_OBJ | ANML_WANT_GRAD, nullptr, m->stream));
     const size_t P = m->P;
     const size_t flag_at = 1 + P + P * P;
     if (want & ANML_WANT_HESS) {
@@ -1504,10 +1752,133 @@ extern "C" int anml_model_eval(anml_model* m, const double* x_host, int want, do
         CU_TRY(cudaMemcpyAsync(m->h_packed + flag_at, m->d_packed + flag_at, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
     }
     CU_TRY(cudaStreamSynchronize(m->stream));
+    m->eval_pending = false;
     if (m->h_packed[flag_at] != 0.0) return fail(ANML_EDOMAIN, "linear predictor outside the domain of a Log/Logit mapping");
     if (want & ANML_WANT_OBJ) *obj = m->h_packed[0];
     if (want & ANML_WANT_GRAD) memcpy(grad, m->h_packed + 1, P * sizeof(double));
     if (want & ANML_WANT_HESS) memcpy(hess, m->h_packed + 1 + P, P * P * sizeof(double));
+    return ANML_OK;
+}
+
+// ----------------------------------------------------------------------------
+// peer-memory all-reduce of the packed record (comm.cuh)
+// ----------------------------------------------------------------------------
+struct anml_comm {
+    int device = 0, rank = 0, world = 1, sm_count = 0;
+    long long max_elems = 0;
+    unsigned long long epoch = 0;
+    unsigned long long* window = nullptr;               // local, cudaMalloc'ed, exported
+    unsigned long long* peer[COMM_MAX_WORLD] = {};       // mapped windows, peer[rank] == window
+    bool connected = false;
+    long long timeout_cycles = 0;
+};
+
+extern "C" int anml_comm_handle_bytes(int* out) {
+    if (!out) return fail(ANML_EINVAL, "NULL argument");
+    *out = (int)sizeof(cudaIpcMemHandle_t);
+    return ANML_OK;
+}
+
+extern "C" int anml_comm_create(int device, int rank, int world, int64_t max_elems, anml_comm** out) {
+    if (!out || world < 1 || world > COMM_MAX_WORLD || rank < 0 || rank >= world || max_elems <= 0)
+        return fail(ANML_EINVAL, "anml_comm_create: need 0 <= rank < world <= %d and max_elems > 0", COMM_MAX_WORLD);
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    anml_comm* c = new (std::nothrow) anml_comm();
+    if (!c) return fail(ANML_ENOMEM, "out of host memory");
+    c->device = device; c->rank = rank; c->world = world; c->max_elems = max_elems; c->sm_count = prop.multiProcessorCount;
+    c->timeout_cycles = (long long)(20.0 * 1e3 * (double)prop.clockRate);  // ~20 s of SM clock (clockRate is in kHz)
+    if (const char* s = getenv("ANML_B200_COMM_TIMEOUT_S")) {
+        const double v = atof(s);
+        if (v > 0.0) c->timeout_cycles = (long long)(v * 1e3 * (double)prop.clockRate);
+    }
+    const size_t bytes = (size_t)COMM_HEADER_U64 * 8 + (size_t)2 * max_elems * sizeof(double);
+    cudaError_t e = cudaMalloc(&c->window, bytes);
+    if (e == cudaSuccess) e = cudaMemset(c->window, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        if (c->window) cudaFree(c->window);
+        delete c;
+        return fail(e == cudaErrorMemoryAllocation ? ANML_ENOMEM : ANML_ECUDA, "anml_comm_create: %s", cudaGetErrorString(e));
+    }
+    c->peer[rank] = c->window;
+    *out = c;
+    return ANML_OK;
+}
+
+extern "C" int anml_comm_export(anml_comm* c, void* handle_out) {
+    if (!c || !handle_out) return fail(ANML_EINVAL, "NULL argument");
+    CU_TRY(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, c->window));
+    memcpy(handle_out, &h, sizeof(h));
+    return ANML_OK;
+}
+
+extern "C" int anml_comm_connect(anml_comm* c, const void* all_handles) {
+    if (!c || !all_handles) return fail(ANML_EINVAL, "NULL argument");
+    if (c->connected) return fail(ANML_ESTATE, "anml_comm_connect: already connected");
+    CU_TRY(cudaSetDevice(c->device));
+    const char* hs = static_cast<const char*>(all_handles);
+    for (int j = 0; j < c->world; ++j) {
+        if (j == c->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hs + (size_t)j * sizeof(h), sizeof(h));
+        void* ptr = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            for (int q = 0; q < j; ++q)
+                if (q != c->rank && c->peer[q]) {
+                    cudaIpcCloseMemHandle(c->peer[q]);
+                    c->peer[q] = nullptr;
+                }
+            return fail(ANML_ECUDA, "cudaIpcOpenMemHandle for rank %d failed: %s", j, cudaGetErrorString(e));
+        }
+        c->peer[j] = static_cast<unsigned long long*>(ptr);
+    }
+    c->connected = true;
+    return ANML_OK;
+}
+
+extern "C" int anml_comm_allreduce_async(anml_comm* c, double* buf_dev, int64_t n_elems, void* stream) {
+    if (!c || !buf_dev) return fail(ANML_EINVAL, "NULL argument");
+    if (!c->connected && c->world > 1) return fail(ANML_ESTATE, "anml_comm_allreduce_async: not connected");
+    if (n_elems <= 0 || n_elems > c->max_elems) return fail(ANML_EINVAL, "anml_comm_allreduce_async: %lld elements, capacity %lld", (long long)n_elems, c->max_elems);
+    CU_TRY(cudaSetDevice(c->device));
+    CommArgs a;
+    memset(&a, 0, sizeof(a));
+    a.buf = buf_dev; a.n = n_elems; a.max_elems = c->max_elems; a.rank = c->rank; a.world = c->world;
+    a.epoch = ++c->epoch; a.local = c->window; a.timeout_cycles = c->timeout_cycles;
+    for (int j = 0; j < c->world; ++j) a.peer[j] = c->peer[j];
+    long long grid = (n_elems + 511) / 512;  // two elements per thread, at most one CTA per SM (all co-resident while waiting)
+    if (grid > c->sm_count) grid = c->sm_count;
+    if (grid < 1) grid = 1;
+    comm_allreduce_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(a);
+    CU_TRY(cudaGetLastError());
+    return ANML_OK;
+}
+
+extern "C" int anml_comm_error(anml_comm* c, int64_t* failed_epoch) {
+    if (!c || !failed_epoch) return fail(ANML_EINVAL, "NULL argument");
+    CU_TRY(cudaSetDevice(c->device));
+    unsigned long long v = 0;
+    CU_TRY(cudaMemcpy(&v, c->window + COMM_MAX_WORLD + 1, sizeof(v), cudaMemcpyDeviceToHost));
+    *failed_epoch = (int64_t)v;
+    return ANML_OK;
+}
+
+extern "C" int anml_comm_destroy(anml_comm* c) {
+    if (!c) return ANML_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int j = 0; j < c->world; ++j)
+        if (j != c->rank && c->peer[j]) cudaIpcCloseMemHandle(c->peer[j]);
+    if (c->window) cudaFree(c->window);
+    (void)cudaGetLastError();
+    delete c;
     return ANML_OK;
 }
 

@@ -20,8 +20,9 @@
 //     A (= X^T) and, scaled by w_k, as B of DMMA.8x8x4; only the 8x8 tiles on or
 //     below the diagonal are computed (NB8*(NB8+1)/2 of NB8^2);  g += r_k a[j].
 //   * epilogue: warps reduce through the (now idle) ring memory, each CTA writes
-//     one partial record; reduce_partials + assemble kernels finish (fixed order,
-//     no floating-point atomics -> bitwise reproducible for a given grid).
+//     one partial record; finish_fused_kernel (finish.cuh) sums the records in a fixed
+//     order and undoes the layout (no floating-point atomics -> bitwise reproducible
+//     for a given grid).
 //
 // Fragment/column mapping: lane (g = lane>>2, t = lane&3) loads, for 16-column
 // group j, the double2 at columns (16j + 2g, 16j + 2g + 1) of row k(t).  8-column
@@ -329,77 +330,6 @@ __global__ void __launch_bounds__(256, 1) fused_eval_kernel(const __grid_constan
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) s += reinterpret_cast<const double*>(ring_all + w * C::RING_BYTES)[e];
         out[e] = s;
-    }
-}
-
-// Sum the per-CTA partial records in a fixed order: reduced[e] = sum_c partials[c][e].
-// 16 independent loads in flight per thread (the loop is latency-bound: 148 records,
-// 2.6k elements), combined in a fixed tree so the result does not depend on timing.
-__global__ void __launch_bounds__(128) reduce_partials_kernel(const double* __restrict__ partials, int ncta, int el,
-                                                              double* __restrict__ reduced) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= el) return;
-    double s[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) s[u] = 0.0;
-    int c = 0;
-    for (; c + 15 < ncta; c += 16) {
-#pragma unroll
-        for (int u = 0; u < 16; ++u) s[u] += partials[(size_t)(c + u) * el + e];
-    }
-    double tail = 0.0;
-    for (; c < ncta; ++c) tail += partials[(size_t)c * el + e];
-    s[0] += tail;
-#pragma unroll
-    for (int w = 8; w >= 1; w >>= 1)
-#pragma unroll
-        for (int u = 0; u < w; ++u) s[u] += s[u + w];
-    reduced[e] = s[0];
-}
-
-// Undo the fragment/tile layout into the packed record
-//     packed = [obj | grad(P_total) | hess(P_total, P_total) row-major | flag].
-// The (symmetric) p x p block lands at (row_off, col_off) of the Hessian and,
-// when that is off the diagonal, also transposed at (col_off, row_off).
-__global__ void __launch_bounds__(256) assemble_kernel(const double* __restrict__ reduced, int nb16, int hess, int p,
-                                                       double* __restrict__ packed, int P_total, int row_off, int col_off,
-                                                       int write_grad, int add_obj) {
-    const int NB8 = 2 * nb16, NT = NB8 * (NB8 + 1) / 2;
-    const int goff = hess ? 2 * NT : 0;
-    double* grad = packed + 1 + row_off;
-    double* H = packed + 1 + P_total;
-    if (threadIdx.x == 0) {
-        double s = 0.0;
-        for (int l = 0; l < 32; ++l) s += reduced[(goff + NB8) * 32 + l];
-        if (add_obj) packed[0] += s; else packed[0] = s;
-    }
-    if (write_grad) {
-        for (int c = threadIdx.x; c < p; c += blockDim.x) {
-            // column c = 16*(jb>>1) + 2*g + (jb&1)
-            const int jb = 2 * (c >> 4) + (c & 1), gg = (c & 15) >> 1;
-            double s = 0.0;
-            for (int tt = 0; tt < 4; ++tt) s += reduced[(goff + jb) * 32 + 4 * gg + tt];
-            grad[c] = s;
-        }
-    }
-    if (!hess) return;
-    for (int e = threadIdx.x; e < 2 * NT * 32; e += blockDim.x) {
-        const int lane = e & 31, reg = (e >> 5) & 1, tile = e >> 6;
-        int I = 0;  // tile = I*(I+1)/2 + J
-        while ((I + 1) * (I + 2) / 2 <= tile) ++I;
-        const int J = tile - I * (I + 1) / 2;
-        const int m = lane >> 2, nn = 2 * (lane & 3) + reg;
-        if (I == J && m < nn) continue;  // keep one triangle of diagonal tiles: exact symmetry
-        const int c1 = 16 * (I >> 1) + 2 * m + (I & 1);
-        const int c2 = 16 * (J >> 1) + 2 * nn + (J & 1);
-        if (c1 >= p || c2 >= p) continue;
-        const double v = reduced[e];
-        H[(size_t)(row_off + c1) * P_total + col_off + c2] = v;
-        H[(size_t)(row_off + c2) * P_total + col_off + c1] = v;
-        if (row_off != col_off) {
-            H[(size_t)(col_off + c2) * P_total + row_off + c1] = v;
-            H[(size_t)(col_off + c1) * P_total + row_off + c2] = v;
-        }
     }
 }
 

@@ -38,8 +38,8 @@
 // every full[] barrier, also for blocks of the other helper (a parity wait cannot tell
 // phases two apart).
 //
-// Partial-record layout is the one of fused_eval_kernel (reduce_partials_kernel
-// and assemble_kernel are shared).
+// Partial-record layout is the one of fused_eval_kernel (finish_fused_kernel, finish.cuh,
+// is the shared one-launch epilogue).
 #pragma once
 #include "common.cuh"
 #include "rowmath.cuh"
@@ -68,7 +68,7 @@ struct HessCfg {
     static constexpr int TEAM_BYTES = NBUF * BUF_BYTES;
     static constexpr int EL = (2 * NT + NB8 + 1) * 32;
     static constexpr int SMEM_BYTES = 1024 + TEAMS * TEAM_BYTES + TEAMS * NBUF * ROWS * 4 /*sign masks*/ + TEAMS * NBUF * 2 * 8 /*full barriers, ready flags*/ +
-                                      16 * NB16 * 8 /*beta*/ + TEAMS * HELPERS * (NB8 + 1) * 32 * 8 /*helper g, obj; transpose scratch*/ +
+                                      2 * 16 * NB16 * 8 /*beta, beta1*/ + TEAMS * HELPERS * (NB8 + 1) * 32 * 8 /*helper g, obj; transpose scratch*/ +
                                       TEAMS * HELPERS * 64 * 8 /*helper r, sqrt|w|*/;
 };
 
@@ -126,7 +126,12 @@ __device__ __forceinline__ void mma_kstep(double* acc, const double* av, uint32_
 }
 
 // MODE 0: per-row terms computed here from X, beta, obs (one-parameter models);
-// MODE 1: (r, w) read from a.rvec / a.wvec (blocks of the general path).
+// MODE 1: (r, w) read from a.rvec / a.wvec (blocks of the general path; rvec == nullptr: no gradient);
+// MODE 3: two parameters over this one design (mean / variance model, BASELINE config #4): the helpers
+//         form BOTH linear predictors, take the row terms of the pair once, accumulate the objective,
+//         g0 = X^T r0 and H00 = X^T diag(w00) X here and leave (r1, w01, w11) in a.out_* for the two
+//         MODE 1 launches that follow -- the separate dual-predictor pass of round 1 (a fourth read of
+//         X) is gone.
 // TMA3D: the tensor map is the 3-D view (16 cols, rows, column groups) and one instruction
 // fetches the whole block (api.cu encodes it when p is a multiple of 16).
 template <int NB16, int NHELP, bool SIGNED, int MODE, bool TMA3D, int ROWS>
@@ -142,7 +147,7 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
     const uint32_t signs_base = smem_base + TEAMS * C::TEAM_BYTES;
     const uint32_t bars_base = signs_base + TEAMS * NBUF * SIGN_BYTES;
     const uint32_t beta_base = bars_base + TEAMS * NBUF * 2 * 8;
-    const uint32_t hrec_base = beta_base + 16 * NB16 * 8;
+    const uint32_t hrec_base = beta_base + 2 * 16 * NB16 * 8;  // [beta | beta1 (MODE 3)]
     const uint32_t hterm_base = hrec_base + TEAMS * C::HELPERS * (NB8 + 1) * 256;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -159,7 +164,10 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
             }
         mbar_fence_init();
     }
-    if (threadIdx.x < 16 * NB16) sts64(beta_base + threadIdx.x * 8, MODE == 0 ? a.beta[threadIdx.x] : 0.0);
+    if (threadIdx.x < 16 * NB16) {
+        sts64(beta_base + threadIdx.x * 8, (MODE == 0 || MODE == 3) ? a.beta[threadIdx.x] : 0.0);
+        sts64(beta_base + (16 * NB16 + threadIdx.x) * 8, MODE == 3 ? a.beta1[threadIdx.x] : 0.0);
+    }
     __syncthreads();
 
     const uint32_t ring_u32 = smem_base + team * C::TEAM_BYTES;
@@ -270,6 +278,7 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
 #pragma unroll
         for (int i = 0; i < NB8; ++i) gacc[i] = 0.0;
         bool bad_domain = false;
+        const bool want_grad = (MODE != 1) || a.rvec != nullptr;
         // lane (g,t) ends up owning the row of k-step s == g, sub-row t
         const int R = 16 * (g >> 2) + 8 * ((g >> 1) & 1) + (g & 1) + 2 * t;
         const uint32_t tr_u32 = hrec_base + (team * C::HELPERS + hid) * (NB8 + 1) * 256;  // transpose scratch (epilogue record later)
@@ -277,7 +286,7 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
         // this lane's slice of beta (columns 16j + 2g, +1) stays in registers
         double2 bsl[NB16];
 #pragma unroll
-        for (int j = 0; j < NB16; ++j) bsl[j] = lds128(beta_base + 2 * g * 8 + j * 128);
+        for (int j = 0; j < NB16; ++j) bsl[j] = lds128(beta_base + 2 * g * 8 + j * 128);  // (MODE 3: beta1 is re-read from shared memory per k-step)
         uint32_t phase_bits = 0;
         int buf = -1;
         for (long long i = 0; i < nmine; ++i) {
@@ -354,8 +363,49 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
                         sc = rt.sw;
                     }
                 }
+            } else if (MODE == 3) {
+                double off0 = 0.0, off1 = 0.0, ob = 0.0;
+                if (valid) {
+                    if (a.offset) off0 = a.offset[row];
+                    if (a.offset1) off1 = a.offset1[row];
+                    ob = a.obs[row];
+                }
+                // ---- pass 1: both linear predictors from one sweep over the block
+                double part0[8], part1[8];
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const int xr = 2 * t + (s & 1);
+                    const int rowi = 16 * (s >> 2) + 8 * ((s >> 1) & 1) + xr;
+                    const uint32_t rp = bp + rowi * 128 + ((g ^ xr) << 4);
+                    double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NB16; ++j) {
+                        const double2 v = lds128(rp + j * GB);
+                        const double2 b1 = lds128(beta_base + (16 * NB16 + 2 * g) * 8 + j * 128);
+                        d0 = fma(v.x, bsl[j].x, d0);
+                        d0 = fma(v.y, bsl[j].y, d0);
+                        d1 = fma(v.x, b1.x, d1);
+                        d1 = fma(v.y, b1.y, d1);
+                    }
+                    part0[s] = d0;
+                    part1[s] = d1;
+                }
+                const double y0 = transpose_reduce8(part0, g) + off0;
+                const double y1 = transpose_reduce8(part1, g) + off1;
+                if (valid) {
+                    const RowTerms2 rt = row_terms2(a.link, a.link1, y0, y1, ob);
+                    bad_domain |= !rt.ok;
+                    const double wt = a.weights ? a.weights[row] : 1.0;
+                    objacc += wt * rt.l;
+                    rr = wt * rt.r0;
+                    ww = wt * rt.w00;
+                    sc = sqrt(fabs(ww));
+                    a.out_r1[row] = wt * rt.r1;
+                    a.out_w01[row] = wt * rt.w01;
+                    a.out_w11[row] = wt * rt.w11;
+                }
             } else if (valid) {
-                rr = a.rvec[row];
+                if (a.rvec) rr = a.rvec[row];
                 ww = a.wvec[row];
                 sc = sqrt(fabs(ww));
             }
@@ -376,8 +426,10 @@ __global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const 
 #pragma unroll
                 for (int j = 0; j < NB16; ++j) {
                     const double2 v = lds128(rp + j * GB);
-                    gacc[2 * j] = fma(rv, v.x, gacc[2 * j]);
-                    gacc[2 * j + 1] = fma(rv, v.y, gacc[2 * j + 1]);
+                    if (MODE != 1 || want_grad) {  // (MODE 1, cross block of two parameters: Hessian only)
+                        gacc[2 * j] = fma(rv, v.x, gacc[2 * j]);
+                        gacc[2 * j + 1] = fma(rv, v.y, gacc[2 * j + 1]);
+                    }
                     sts128(rp + j * GB, sv * v.x, sv * v.y);
                 }
             }

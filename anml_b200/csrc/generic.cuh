@@ -324,7 +324,11 @@ __global__ void fill_kernel(double* p, long long n, double v) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
 
-__global__ void set_flag_kernel(double* dst, const int* status) { dst[0] = (double)(*status); }
+// publish the Log/Logit domain flag of this evaluation and re-arm the status word for the next one
+__global__ void set_flag_kernel(double* dst, int* status) {
+    dst[0] = (double)(*status);
+    *status = 0;
+}
 
 // scatter `ncols` columns from src (row stride src_ld) into X columns [col0, col0+ncols)
 __global__ void __launch_bounds__(256) scatter_columns_kernel(double* __restrict__ X, long long n, long long ld, int col0,

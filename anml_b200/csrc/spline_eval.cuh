@@ -3,223 +3,205 @@
 // A row of a spline design has degree+1 non-zeros, so the dense path (build the (n, nb) matrix,
 // stream it through the DMMA kernel) moves 8*nb bytes per row to do (degree+1)^2 useful
 // multiply-adds.  Here the basis is evaluated on the fly from x ("for C3 with
-// on-the-fly basis P_X = 1, i.e. just x"): per row one interval lookup, the degree+1 non-zero basis
-// values, the row terms and degree+1 + (degree+1)(degree+2)/2 FMAs into the band block of its knot
-// interval.  The kernel is bound by FP64 instruction issue (B200 has 64 FP64 lanes per SM), so the
-// basis is NOT run through the Cox-de Boor divisions per row: on one knot interval every basis
-// function is a polynomial of degree `degree`, whose Taylor coefficients about the interval's left
-// knot are tabulated once per spline (banded_coeff_kernel, from the same local_basis_ders as the design
-// kernel: c_k = N^(k)(t_idx) / k!) and evaluated by Horner -- degree FMAs per basis value instead of
-// ~150 FP64 instructions per row.  The values agree with the design kernel's to rounding (1e-16), not
-// bit for bit; the design matrix itself is still produced by spline.cuh.
+// on-the-fly basis P_X = 1, i.e. just x"); the kernel reads 8*(1 + #row vectors) bytes per row and
+// is meant to be HBM-bound.
 //
-// No floating-point atomics: the rows are sorted by x once at attach (radix sort of (x, row)),
-// every warp owns a contiguous range of the sorted rows, so the interval index is non-decreasing
-// along its range; a lane keeps the band block of the current interval in registers, and when
-// the warp moves to the next interval the 32 lane blocks are reduced in a fixed order and
-// written to the warp's partial record (each (warp, interval) slot is written at most once).
-// Records are summed over warps in warp order: results are bitwise reproducible.
+// Round-2 formulation (the round-1 kernel did a per-row interval search and kept a band block per
+// lane; it was bound by instruction issue at 0.28 of the HBM roofline):
+//   * the rows are sorted by x once at attach (radix sort of (x, row)), and the first sorted row of
+//     every knot interval is found once (banded_segments_kernel, a binary search per knot), so a
+//     knot interval is a CONTIGUOUS run of rows;
+//   * every CTA owns an equal, contiguous slice of the sorted rows and walks the (one or two) knot
+//     intervals that cross it: inside a run nothing depends on the row -- no search, no flush;
+//   * on one interval every basis function is a polynomial of degree d in u = x - knot_left
+//     (Taylor coefficients c[q][j] tabulated once per spline by banded_coeff_kernel from the same
+//     local_basis_ders as the design kernel).  So the linear predictor is ONE polynomial
+//     y = sum_j (sum_q c[q][j] beta[k+q]) u^j (d FMAs, coefficients folded per run), and the
+//     gradient / Hessian band of the interval are linear in the power moments
+//         G_j = sum_i r_i u_i^j   (j = 0..d)        M_s = sum_i w_i u_i^s   (s = 0..2d)
+//     -- 3d+2 FMAs per row instead of (d+1) + (d+1)(d+2)/2 + the d(d+1) of the basis values.
+//     banded_finish_kernel maps the reduced moments to the band:
+//         grad[k+q] += sum_j c[q][j] G_j,   H[k+p][k+q] += sum_{a,b} c[p][a] c[q][b] M_{a+b}.
+//     The change of basis costs a few bits (|c| u^j terms of alternating sign, ~35x the result),
+//     i.e. ~1e-14 relative: two orders inside the 1e-10 / 1e-9 parity tolerances;
+//   * two rows per thread per load (16-byte loads), next iteration's loads issued before the
+//     current rows are processed;
+//   * one partial record per CTA, one entry per (interval, moment): CTA-level reduction once per
+//     run, records summed over CTAs in a fixed order (banded_reduce_kernel).  No floating-point
+//     atomics, no memset of the records (every CTA writes its whole record): bitwise reproducible.
 #pragma once
 #include "common.cuh"
+#include "finish.cuh"
 #include "rowmath.cuh"
 #include "spline.cuh"
 
 namespace anml {
 
 struct BandedArgs {
-    const double* xs;       // abscissae, sorted ascending (n)
+    const double* xs;       // abscissae, sorted ascending; n rounded up to even (+2) doubles allocated
     const double* obs;      // per-row vectors gathered into the same order (se / offset / weights may be null)
     const double* se;
     const double* offset;
     const double* weights;
     long long n;
-    const double* t;        // clamped knot vector, nk + 2*degree entries
+    const double* knots;    // nk knots (device)
     const double* coef;     // [nk-1][degree+1 bases][degree+1 powers] Taylor coefficients about the left knot
-    int coef_in_smem;       // the table is copied to shared memory when it is small enough
+    const long long* seg;   // [nk] first sorted row of interval k (seg[0] = 0, seg[nk-1] = n)
     int nk;
     const double* beta;     // nb = nk - 1 + degree coefficients
-    int family, link, fast, want_hess;
-    long long rows_per_warp;  // multiple of 32
-    double* partials;       // [warps][rec], rec = (nk-1) * slots + 1, zeroed before the launch
+    int family, link, fast;
+    long long rows_per_cta; // even
+    double* partials;       // [gridDim.x][rec], rec = (nk-1) * NM + 1
     int* status;
 };
 
 template <int DEG>
 struct BandedCfg {
-    static constexpr int NG = DEG + 1;
-    static constexpr int NH = (DEG + 1) * (DEG + 2) / 2;
-    static constexpr int SLOTS = NG + NH;  // per interval: gradient entries, then the lower triangle row by row
+    static constexpr int NG = DEG + 1;       // gradient moments
+    static constexpr int NH = 2 * DEG + 1;   // Hessian moments
+    static constexpr int NM = NG + NH;       // per interval
+    static constexpr int THREADS = 256;
 };
 
-// COEF_SMEM: the coefficient table fits in shared memory (LDS.128 instead of generic loads);
-// HESS: the Hessian band is wanted -- both compile-time, the row loop is bound by instruction issue.
-template <int DEG, bool COEF_SMEM, bool HESS>
-__global__ void __launch_bounds__(256, 2) spline_banded_eval_kernel(const BandedArgs a) {
+// EXTRAS: any of obs_se / offset / weights is present (compile-time, so that the plain case -- x and obs
+// only, BASELINE config #3 -- keeps two loads per row pair and a small register footprint)
+template <int DEG, bool HESS, bool EXTRAS>
+__global__ void __launch_bounds__(256, EXTRAS ? 2 : 3) spline_banded_eval_kernel(const BandedArgs a) {
     using C = BandedCfg<DEG>;
-    extern __shared__ __align__(16) double sm_banded[];
-    const int nt = a.nk + 2 * DEG;
-    const int nb = a.nk - 1 + DEG;
-    double* t_s = sm_banded;
-    double* beta_s = sm_banded + ((nt + 1) & ~1);
-    double* coef_s = beta_s + ((nb + 1) & ~1);
-    for (int i = threadIdx.x; i < nt; i += blockDim.x) t_s[i] = a.t[i];
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) beta_s[i] = a.beta[i];
-    if (COEF_SMEM)
-        for (int i = threadIdx.x; i < (a.nk - 1) * (DEG + 1) * (DEG + 1); i += blockDim.x) coef_s[i] = a.coef[i];
-    __syncthreads();
-    const double* knots = t_s + DEG;
-    const uint32_t coef_u32 = smem_u32(coef_s);
+    constexpr int NG = C::NG, NH = C::NH, NM = C::NM;
+    __shared__ double red[8][NM + 1];
+    const int nint = a.nk - 1;
+    const int rec = nint * NM + 1;
+    double* out = a.partials + (size_t)blockIdx.x * rec;
+    for (int i = threadIdx.x; i < rec; i += blockDim.x) out[i] = 0.0;  // intervals this CTA never meets
 
-    const int lane = threadIdx.x & 31;
-    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long lo = warp * a.rows_per_warp;
-    long long hi = lo + a.rows_per_warp;
+    const long long lo = (long long)blockIdx.x * a.rows_per_cta;
+    long long hi = lo + a.rows_per_cta;
     if (hi > a.n) hi = a.n;
-    const int rec = (a.nk - 1) * C::SLOTS + 1;
-    double* out = a.partials + warp * rec;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double2* xs2 = reinterpret_cast<const double2*>(a.xs);
+    const double2* ob2 = reinterpret_cast<const double2*>(a.obs);
+    const double2* se2 = reinterpret_cast<const double2*>(a.se);
+    const double2* of2 = reinterpret_cast<const double2*>(a.offset);
+    const double2* wt2 = reinterpret_cast<const double2*>(a.weights);
+    const bool has_se = EXTRAS && a.se != nullptr, has_off = EXTRAS && a.offset != nullptr, has_wt = EXTRAS && a.weights != nullptr;
 
-    double accG[C::NG], accH[C::NH];
-#pragma unroll
-    for (int q = 0; q < C::NG; ++q) accG[q] = 0.0;
-#pragma unroll
-    for (int q = 0; q < C::NH; ++q) accH[q] = 0.0;
     double objacc = 0.0;
     bool bad_domain = false;
-    int cur = -1;
+    __syncthreads();  // the zero fill above is ordered before the run results below
 
-    auto flush = [&]() {
-        // fixed-order butterfly over the 32 lane blocks, then lane q writes slot q
-        double mine = 0.0;
-#pragma unroll
-        for (int q = 0; q < C::NG; ++q) {
-            const double v = warp_sum(accG[q]);
-            if (lane == q) mine = v;
-            accG[q] = 0.0;
-        }
-        if (HESS) {
-#pragma unroll
-            for (int q = 0; q < C::NH; ++q) {
-                const double v = warp_sum(accH[q]);
-                if (lane == C::NG + q) mine = v;
-                accH[q] = 0.0;
-            }
-        }
-        if (lane < C::SLOTS) out[cur * C::SLOTS + lane] = mine;
-    };
-
-    // per-row work: interval lookup, basis, linear predictor, row terms
-    // `idx` enters as the interval of the lane's previous row: x is sorted, so the search
-    // clip(#(knots <= x) - 1, 0, nk-2) only ever moves forward (usually by 0 or 1 comparisons)
-    struct RowIn {
-        double x, ob, se, off, wt;
-    };
-    auto load = [&](long long i, bool active) {
-        RowIn r;
-        r.x = 0.0; r.ob = 0.0; r.se = 1.0; r.off = 0.0; r.wt = 1.0;
-        if (active) {
-            r.x = a.xs[i];
-            r.ob = a.obs[i];
-            if (a.se) r.se = a.se[i];
-            if (a.offset) r.off = a.offset[i];
-            if (a.weights) r.wt = a.weights[i];
-        }
-        return r;
-    };
-    auto compute = [&](const RowIn& in, bool active, int& idx, double* N, double& rr, double& ww) {
-        if (!active) return;  // N, rr, ww of an inactive lane are never read
-        const double x = in.x;
-        while (idx < a.nk - 2 && knots[idx + 1] <= x) ++idx;
-        const double u = x - knots[idx];
-        const int cbase = idx * (DEG + 1) * (DEG + 1);
-#pragma unroll
-        for (int q = 0; q <= DEG; ++q) {
-            double ck[DEG + 1];
-            if (COEF_SMEM && (DEG + 1) % 2 == 0) {  // coefficient rows are 16-byte aligned: LDS.128
-#pragma unroll
-                for (int k = 0; k <= DEG; k += 2) {
-                    const double2 v2 = lds128(coef_u32 + (cbase + q * (DEG + 1) + k) * 8);
-                    ck[k] = v2.x;
-                    ck[k + 1] = v2.y;
-                }
-            } else if (COEF_SMEM) {
-#pragma unroll
-                for (int k = 0; k <= DEG; ++k) ck[k] = lds64(coef_u32 + (cbase + q * (DEG + 1) + k) * 8);
-            } else {
-#pragma unroll
-                for (int k = 0; k <= DEG; ++k) ck[k] = __ldg(a.coef + cbase + q * (DEG + 1) + k);
-            }
-            double v = ck[DEG];
-#pragma unroll
-            for (int k = DEG - 1; k >= 0; --k) v = fma(v, u, ck[k]);
-            N[q] = v;
-        }
-        double y = in.off;
-#pragma unroll
-        for (int q = 0; q <= DEG; ++q) y = fma(N[q], beta_s[idx + q], y);
-        const RowTerms1 rt = row_terms1<false>(a.family, a.link, a.fast != 0, y, in.ob, in.se);
-        bad_domain |= !rt.ok;
-        if (a.weights) {
-            const double wt = in.wt;
-            objacc += wt * rt.l;
-            rr = wt * rt.r;
-            ww = wt * rt.w;
-        } else {
-            objacc += rt.l;
-            rr = rt.r;
-            ww = rt.w;
-        }
-    };
-    // lanes of one interval accumulate together; the warp walks the (few) distinct intervals in order
-    auto add_row = [&](const double* N, double rr, double ww) {
-#pragma unroll
-        for (int q = 0; q <= DEG; ++q) accG[q] = fma(rr, N[q], accG[q]);
-        if (HESS) {
-#pragma unroll
-            for (int p = 0; p <= DEG; ++p) {
-                const double wp = ww * N[p];
-#pragma unroll
-                for (int q = 0; q <= p; ++q) accH[p * (p + 1) / 2 + q] = fma(wp, N[q], accH[p * (p + 1) / 2 + q]);
-            }
-        }
-    };
-    auto accumulate = [&](bool active, int idx, const double* N, double rr, double ww) {
-        // common case: every active lane is still in the warp's current interval
-        if (__all_sync(FULL_MASK, !active || idx == cur)) {
-            if (active) add_row(N, rr, ww);
-            return;
-        }
-        unsigned todo = __ballot_sync(FULL_MASK, active);
-        while (todo) {
-            const int leader = __ffs(todo) - 1;
-            const int v = __shfl_sync(FULL_MASK, idx, leader);
-            const bool mine = active && idx == v;
-            if (v != cur) {
-                if (cur >= 0) flush();
-                cur = v;
-            }
-            if (mine) add_row(N, rr, ww);
-            todo &= ~__ballot_sync(FULL_MASK, mine);
-        }
-    };
-    // The row loop is bound by the latency of its global loads (ncu: long-scoreboard stalls, FP64 pipe
-    // 15 % busy), and 118 registers allow only 16 warps per SM: the inputs of the next two iterations
-    // are fetched into registers before the current one is processed.
-    int idx = 0;
-    RowIn in0 = load(lo + lane, lo + lane < hi);
-    RowIn in1 = load(lo + 32 + lane, lo + 32 + lane < hi);
-    for (long long base = lo; base < hi; base += 32) {
-        const long long i = base + lane;
-        const bool active = i < hi;
-        const RowIn in2 = load(i + 64, i + 64 < hi);
-        double N[DEG + 1], rr, ww;
-        compute(in0, active, idx, N, rr, ww);
-        accumulate(active, idx, N, rr, ww);
-        in0 = in1;
-        in1 = in2;
+    int k = 0;
+    if (lo < hi) {
+        while (k < nint - 1 && a.seg[k + 1] <= lo) ++k;
     }
-    if (cur >= 0) flush();
-    const double o = warp_sum(objacc);
-    if (lane == 0) out[rec - 1] = o;
+    for (; lo < hi && k < nint; ++k) {
+        const long long sa = a.seg[k], sb = a.seg[k + 1];
+        if (sa >= hi) break;
+        const long long ra = sa > lo ? sa : lo, rb = sb < hi ? sb : hi;
+        if (ra >= rb) continue;  // empty interval (repeated knots)
+        // ---- per-run constants: left knot, polynomial of the linear predictor
+        const double knot = a.knots[k];
+        double d[DEG + 1];
+#pragma unroll
+        for (int j = 0; j <= DEG; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q <= DEG; ++q) s = fma(a.coef[(k * (DEG + 1) + q) * (DEG + 1) + j], a.beta[k + q], s);
+            d[j] = s;
+        }
+        double G[NG], M[NH];
+#pragma unroll
+        for (int j = 0; j < NG; ++j) G[j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NH; ++j) M[j] = 0.0;
+
+        auto row = [&](double x, double ob, double se, double off, double wt) {
+            const double u = x - knot;
+            double y = d[DEG];
+#pragma unroll
+            for (int j = DEG - 1; j >= 0; --j) y = fma(y, u, d[j]);
+            const RowTerms1 rt = row_terms1<false>(a.family, a.link, a.fast != 0, y + off, ob, se);
+            bad_domain |= !rt.ok;
+            double l = rt.l, r = rt.r, w = rt.w;
+            if (has_wt) {
+                l *= wt; r *= wt; w *= wt;
+            }
+            objacc += l;
+            double pw[NH];  // u^s
+            pw[0] = 1.0;
+            if (NH > 1) pw[1] = u;
+#pragma unroll
+            for (int s = 2; s < NH; ++s) pw[s] = pw[s >> 1] * pw[s - (s >> 1)];
+            G[0] += r;
+#pragma unroll
+            for (int j = 1; j < NG; ++j) G[j] = fma(r, pw[j], G[j]);
+            if (HESS) {
+                M[0] += w;
+#pragma unroll
+                for (int s = 1; s < NH; ++s) M[s] = fma(w, pw[s], M[s]);
+            }
+        };
+        struct Pair {
+            double2 x, ob, se, off, wt;  // (se, off, wt fold to constants without EXTRAS)
+        };
+        auto load = [&](long long p, bool live) {
+            Pair q;
+            q.x = make_double2(0.0, 0.0); q.ob = q.x; q.off = q.x;
+            q.se = make_double2(1.0, 1.0); q.wt = q.se;
+            if (live) {
+                q.x = xs2[p];
+                q.ob = ob2[p];
+                if (EXTRAS) {
+                    if (has_se) q.se = se2[p];
+                    if (has_off) q.off = of2[p];
+                    if (has_wt) q.wt = wt2[p];
+                }
+            }
+            return q;
+        };
+        // pairs (2p, 2p+1) that overlap [ra, rb); only the first and last pair can be partial
+        const long long p0 = ra >> 1, p1 = (rb + 1) >> 1;
+        long long p = p0 + threadIdx.x;
+        Pair cur = load(p, p < p1);
+        for (; p < p1; p += C::THREADS) {
+            const Pair nxt = load(p + C::THREADS, p + C::THREADS < p1);
+            const long long i0 = 2 * p;
+            if (i0 >= ra) row(cur.x.x, cur.ob.x, cur.se.x, cur.off.x, cur.wt.x);
+            if (i0 + 1 < rb) row(cur.x.y, cur.ob.y, cur.se.y, cur.off.y, cur.wt.y);
+            cur = nxt;
+        }
+        // ---- CTA reduction of the run's moments (fixed order) -> record
+#pragma unroll
+        for (int j = 0; j < NG; ++j) G[j] = warp_sum(G[j]);
+        if (HESS) {
+#pragma unroll
+            for (int j = 0; j < NH; ++j) M[j] = warp_sum(M[j]);
+        }
+        __syncthreads();  // red[] of the previous run has been read
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < NG; ++j) red[warp][j] = G[j];
+#pragma unroll
+            for (int j = 0; j < NH; ++j) red[warp][NG + j] = HESS ? M[j] : 0.0;
+        }
+        __syncthreads();
+        if (threadIdx.x < NM) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+            out[k * NM + threadIdx.x] = s;
+        }
+    }
+    objacc = warp_sum(objacc);
+    __syncthreads();
+    if (lane == 0) red[warp][NM] = objacc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][NM];
+        out[rec - 1] = s;
+    }
     if (bad_domain) atomicOr(a.status, 1);
 }
 
@@ -238,10 +220,33 @@ __global__ void banded_coeff_kernel(const double* __restrict__ t, int nk, double
     for (int q = 0; q <= DEG; ++q) coef[idx * (DEG + 1) * (DEG + 1) + q * (DEG + 1) + k] = N[q] / fact;
 }
 
-// partial records summed over warps in a fixed order: a 32 x 32 block owns 32 entries, row ty of the
-// block walks the warps ty, ty + 32, ... (loads coalesce across the entries), then the 32 row sums are
-// added in order.  (One thread per entry walking all 2368 records serially took 0.3 ms.)
-__global__ void __launch_bounds__(1024) banded_reduce_kernel(const double* __restrict__ partials, long long nwarps, int rec,
+// seg[k] = first sorted row with x >= knots[k] (k = 1..nk-2), seg[0] = 0, seg[nk-1] = n: rows of interval
+// k are [seg[k], seg[k+1]) -- the same integer as clip(searchsorted(knots, x, "right") - 1, 0, nk-2)
+__global__ void banded_segments_kernel(const double* __restrict__ xs, long long n, const double* __restrict__ knots, int nk,
+                                       long long* __restrict__ seg) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nk) return;
+    if (k == 0) {
+        seg[0] = 0;
+        return;
+    }
+    if (k == nk - 1) {
+        seg[k] = n;
+        return;
+    }
+    const double kn = knots[k];
+    long long lo = 0, hi = n;  // first index with xs[i] >= kn
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (xs[mid] < kn) lo = mid + 1; else hi = mid;
+    }
+    seg[k] = lo;
+}
+
+// partial records summed over CTAs in a fixed order: a 32 x 32 block owns 32 entries, row ty of the
+// block walks the records ty, ty + 32, ... (loads coalesce across the entries), then the 32 row sums are
+// added in order.
+__global__ void __launch_bounds__(1024) banded_reduce_kernel(const double* __restrict__ partials, long long nrec, int rec,
                                                             double* __restrict__ reduced) {
     __shared__ double part[32][33];
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -249,11 +254,11 @@ __global__ void __launch_bounds__(1024) banded_reduce_kernel(const double* __res
     double s0 = 0.0, s1 = 0.0;
     if (e < rec) {
         long long w = ty;
-        for (; w + 32 < nwarps; w += 64) {
+        for (; w + 32 < nrec; w += 64) {
             s0 += partials[w * rec + e];
             s1 += partials[(w + 32) * rec + e];
         }
-        if (w < nwarps) s0 += partials[w * rec + e];
+        if (w < nrec) s0 += partials[w * rec + e];
     }
     part[ty][tx] = s0 + s1;
     __syncthreads();
@@ -265,29 +270,83 @@ __global__ void __launch_bounds__(1024) banded_reduce_kernel(const double* __res
     }
 }
 
-// band blocks -> packed [obj | grad(P) | hess(P x P)]: entry (i, j) gathers the intervals that hold both bases
-__global__ void __launch_bounds__(256) banded_assemble_kernel(const double* __restrict__ reduced, int nint, int deg, int hess,
-                                                             double* __restrict__ packed, int P) {
-    const int ng = deg + 1, slots = ng + (deg + 1) * (deg + 2) / 2;
-    const int total = 1 + P + (hess ? P * P : 0);
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-        if (e == 0) {
-            packed[0] = reduced[nint * slots];
-        } else if (e <= P) {
-            const int i = e - 1;
+// reduced moments -> packed [obj | grad(P) | hess(P x P) | flag], Gaussian prior terms and the domain
+// flag included (one launch; round 1 used assemble + add_priors + set_flag).  One thread per packed
+// entry; entry (i, j) gathers the intervals that hold both bases.
+struct BandedFinishArgs {
+    const double* reduced;  // [(nk-1) * NM + 1]
+    const double* coef;     // [nk-1][deg+1][deg+1]
+    int nint, deg, hess, P;
+    double* packed;
+    const double* beta;
+    PriorDev prior;
+    int* status;
+};
+
+__global__ void __launch_bounds__(256) banded_finish_kernel(const BandedFinishArgs a) {
+    extern __shared__ double res_s[];  // unscaled residuals of the linear prior rows (gradient / objective CTA)
+    const int deg = a.deg, ng = deg + 1, nm = ng + 2 * deg + 1, P = a.P;
+    const int total = 1 + P + (a.hess ? P * P : 0);
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool lin = a.prior.on && a.prior.m > 0;
+    if (lin && (long long)blockIdx.x * blockDim.x < 1 + P) {  // CTA-uniform
+        for (int i = threadIdx.x; i < a.prior.m; i += blockDim.x) {
             double s = 0.0;
-            for (int idx = (i - deg > 0 ? i - deg : 0); idx <= i && idx < nint; ++idx) s += reduced[idx * slots + (i - idx)];
-            packed[e] = s;
-        } else {
-            const int i = (e - 1 - P) / P, j = (e - 1 - P) % P;
-            const int hi = i > j ? i : j, lo = i > j ? j : i;
-            double s = 0.0;
-            for (int idx = (hi - deg > 0 ? hi - deg : 0); idx <= lo && idx < nint; ++idx) {
-                const int p = hi - idx, q = lo - idx;
-                s += reduced[idx * slots + ng + p * (p + 1) / 2 + q];
-            }
-            packed[e] = s;
+            for (int j = 0; j < P; ++j) s = fma(a.prior.lin_mat[(size_t)i * P + j], a.beta[j], s);
+            res_s[i] = s - a.prior.lin_mean[i];
         }
+        __syncthreads();
+    }
+    if (e >= total) return;
+    if (e == 0) {
+        double o = a.reduced[a.nint * nm];
+        if (a.prior.on) {
+            for (int j = 0; j < P; ++j) {
+                const double dd = a.beta[j] - a.prior.mean[j];
+                o += 0.5 * dd * dd * a.prior.inv_var[j];
+            }
+            for (int i = 0; i < a.prior.m; ++i) o += 0.5 * res_s[i] * res_s[i] * a.prior.lin_inv_var[i];
+        }
+        a.packed[0] = o;
+        a.packed[1 + P + (size_t)P * P] = (double)(*a.status);
+        *a.status = 0;
+    } else if (e <= P) {
+        const int i = e - 1;
+        double s = 0.0;
+        for (int k = (i - deg > 0 ? i - deg : 0); k <= i && k < a.nint; ++k) {
+            const double* c = a.coef + (k * ng + (i - k)) * ng;
+            const double* Gk = a.reduced + k * nm;
+            double v = 0.0;
+            for (int j = 0; j < ng; ++j) v = fma(c[j], Gk[j], v);
+            s += v;
+        }
+        if (a.prior.on) {
+            double pg = (a.beta[i] - a.prior.mean[i]) * a.prior.inv_var[i];
+            for (int r = 0; r < a.prior.m; ++r) pg = fma(a.prior.lin_mat[(size_t)r * P + i], res_s[r] * a.prior.lin_inv_var[r], pg);
+            s += pg;
+        }
+        a.packed[e] = s;
+    } else {
+        const int i = (e - 1 - P) / P, j = (e - 1 - P) % P;
+        const int hi = i > j ? i : j, lo = i > j ? j : i;
+        double s = 0.0;
+        for (int k = (hi - deg > 0 ? hi - deg : 0); k <= lo && k < a.nint; ++k) {
+            const double* cp = a.coef + (k * ng + (hi - k)) * ng;
+            const double* cq = a.coef + (k * ng + (lo - k)) * ng;
+            const double* Mk = a.reduced + k * nm + ng;
+            double v = 0.0;
+            for (int x = 0; x < ng; ++x) {
+                double t = 0.0;
+                for (int y = 0; y < ng; ++y) t = fma(cq[y], Mk[x + y], t);
+                v = fma(cp[x], t, v);
+            }
+            s += v;
+        }
+        if (a.prior.on) {
+            if (a.prior.m > 0) s += a.prior.lin_hess[(size_t)hi * P + lo];
+            if (i == j) s += a.prior.inv_var[i];
+        }
+        a.packed[e] = s;  // (i, j) and (j, i) evaluate the same expression: exactly symmetric
     }
 }
 

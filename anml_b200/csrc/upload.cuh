@@ -126,8 +126,11 @@ static cudaError_t upload_run(int device, int sm_count, const UploadJob& job) {
     if (e != cudaSuccess) return e;
     if (nthreads > (int)pool.lanes.size()) nthreads = (int)pool.lanes.size();
 
-    // the destination may still be read by work queued earlier on other streams
-    e = cudaDeviceSynchronize();
+    // The lanes' streams are non-blocking: they do not order themselves behind the legacy default stream,
+    // where the callers' cudaMemset of a fresh destination runs.  Wait for that stream only -- a
+    // device-wide synchronisation here would stall unrelated streams (another model evaluating on this
+    // GPU); callers that re-upload into a buffer an evaluation may still read quiesce the model first.
+    e = cudaStreamSynchronize(cudaStreamLegacy);
     if (e != cudaSuccess) return e;
 
     const bool dense = job.col0 == 0 && job.dst_ld == job.ncols;
@@ -180,6 +183,19 @@ static cudaError_t upload_run(int device, int sm_count, const UploadJob& job) {
         for (auto& t : threads) t.join();
     }
     return (cudaError_t)first_error.load();
+}
+
+// free the lanes of one device (pinned + device staging buffers, streams); they are rebuilt on demand
+static void upload_release_device(int device) {
+    if (device < 0 || device >= UPLOAD_MAX_DEVICES) return;
+    UploadPool& pool = g_upload_pools[device];
+    std::lock_guard<std::mutex> guard(pool.mu);
+    if (pool.lanes.empty()) return;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return;
+    }
+    upload_pool_release(pool);
 }
 
 // contiguous host vector -> contiguous device vector

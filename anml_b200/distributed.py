@@ -2,14 +2,25 @@
 
 Rows are independent units and every quantity is a sum over rows, so rank ``r``
 of ``W`` owns the contiguous block ``[r*n//W, (r+1)*n//W)`` of X / obs / offset
-and evaluates it with the same fused kernel.  The only exchange is one
-``all_reduce(SUM)`` of the packed record ``[obj | grad(P) | hess(P*P) | flag]``
-per evaluation (33 KB at P = 64) over NCCL / NVLink; the Gaussian prior is
-added on rank 0 only, before the reduce, so it is counted once.
+and evaluates it with the same fused kernel.  The only exchange is one sum of
+the packed record ``[obj | grad(P) | hess(P*P) | flag]`` per evaluation (33 KB
+at P = 64); the Gaussian prior is added on rank 0 only, before the reduce, so it
+is counted once.
 
-One process per GPU (``torchrun``); ``torch.distributed`` is the plumbing.  The
-solver runs on rank 0 (``fit``); the other ranks sit in ``serve()`` and evaluate
-whatever coefficient vector rank 0 broadcasts.
+One process per GPU (``torchrun``); ``torch.distributed`` is the plumbing
+(rendezvous, the handle exchange, barriers).  On the evaluation path itself:
+
+* the sum runs over **peer memory**: one kernel per evaluation reads every
+  rank's record through NVLink in rank order (``csrc/comm.cuh``,
+  :class:`PeerAllReduce`) -- about half the latency of the NCCL all-reduce it
+  replaces, and every rank gets the same bits.  ``ANML_B200_COLLECTIVE=nccl``
+  (or a failed peer mapping) selects ``dist.all_reduce`` instead;
+* rank 0 hands the coefficient vector to the serving ranks through a host
+  shared-memory mailbox (:class:`ShmMailbox`; one node, so ``/dev/shm`` reaches
+  everybody) instead of an NCCL broadcast plus a device-to-host copy per rank.
+
+The solver runs on rank 0 (``fit``); the other ranks sit in ``serve()`` and
+evaluate whatever coefficient vector rank 0 posts.
 
 The local evaluator is injected, so the collective logic is exercised on CPU
 (gloo, world_size 2) in ``tests/test_distributed_cpu.py`` with a checker
@@ -29,6 +40,118 @@ def shard_rows(n: int, world: int, rank: int) -> Tuple[int, int]:
     if not (0 <= rank < world):
         raise ValueError("rank outside the world")
     return (rank * n) // world, ((rank + 1) * n) // world
+
+
+class PeerAllReduce:
+    """Sum of a CUDA tensor over the ranks through mapped peer memory (``anml_comm``).
+
+    Construction is collective: every rank exports its window, the handles travel through
+    ``torch.distributed`` once, every rank maps its peers, and a barrier makes sure nobody
+    launches before everybody is mapped."""
+
+    def __init__(self, device_index: int, max_elems: int, group=None):
+        import torch
+        import torch.distributed as dist
+
+        from . import _native
+
+        self.group = group
+        self.torch_float64 = torch.float64
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        self.comm = _native.PeerComm(device_index, rank, world, max_elems)
+        dev = torch.device("cuda", device_index)
+        mine = torch.frombuffer(bytearray(self.comm.export()), dtype=torch.uint8).to(dev)
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)
+        handles = b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts)
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        try:
+            self.comm.connect(handles)
+        except Exception:
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # also the barrier: everybody is mapped
+        if int(ok.item()) == 0:
+            self.comm.free()
+            raise RuntimeError("peer-memory mapping failed on at least one rank")
+        self.device = dev
+
+    def all_reduce(self, tensor, stream_ptr: int):
+        if tensor.dtype != self.torch_float64 or not tensor.is_contiguous():
+            raise TypeError("peer all-reduce takes a contiguous float64 CUDA tensor")
+        self.comm.allreduce_async(tensor.data_ptr(), tensor.numel(), stream_ptr)
+
+    def check(self):
+        e = self.comm.failed_epoch()
+        if e:
+            raise RuntimeError(f"peer all-reduce: a rank did not arrive for evaluation {e} (timeout)")
+
+    def close(self):
+        import torch.distributed as dist
+
+        if dist.is_initialized():
+            dist.barrier(group=self.group)  # nobody still reads this rank's window
+        self.comm.free()
+
+
+class ShmMailbox:
+    """[seq | op | x(P)] in host shared memory: rank 0 posts, the other ranks of the node poll.
+
+    Construction is collective (the segment name travels through ``torch.distributed``).  The
+    sequence number is written last and read first; x86's store order makes that sufficient."""
+
+    def __init__(self, P: int, group=None):
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+
+        self.rank = dist.get_rank(group)
+        self.P = P
+        nbytes = 8 * (2 + P)
+        name = [None]
+        if self.rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            name[0] = self.shm.name
+        dist.broadcast_object_list(name, src=0, group=group)
+        if self.rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+            try:  # the creator unlinks; keep Python's resource tracker of this process out of it
+                from multiprocessing import resource_tracker
+
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.buf = np.ndarray((2 + P,), dtype=np.float64, buffer=self.shm.buf)
+        if self.rank == 0:
+            self.buf[:] = 0.0
+        dist.barrier(group=group)
+        self.seq = 0.0
+
+    def post(self, op: float, x: Optional[np.ndarray]):
+        self.buf[1] = op
+        if x is not None:
+            self.buf[2:] = x
+        self.seq += 1.0
+        self.buf[0] = self.seq
+
+    def wait(self):
+        import time
+
+        want = self.seq + 1.0
+        spins = 0
+        while self.buf[0] < want:
+            spins += 1
+            if spins > 20000:  # ~ms of idling: stop burning the core while the solver thinks
+                time.sleep(0.0002)
+        self.seq = want
+        return float(self.buf[1]), self.buf[2:].copy()
+
+    def close(self):
+        self.buf = None
+        try:
+            self.shm.close()
+            if self.rank == 0:
+                self.shm.unlink()
+        except Exception:
+            pass
 
 
 class NativeLocalEvaluator:
@@ -51,9 +174,11 @@ class NativeLocalEvaluator:
         want = _native.WANT_OBJ | _native.WANT_GRAD | (_native.WANT_HESS if want_hessian else 0)
         # torch's default stream has handle 0, which the C-ABI reads as "the model's own
         # stream"; cudaStreamLegacy (0x1) names the legacy default stream explicitly
-        stream = self.torch.cuda.current_stream(self.device).cuda_stream or 1
-        self.model.native.eval_async(x, want, self.packed.data_ptr(), stream)
+        self.model.native.eval_async(x, want, self.packed.data_ptr(), self.stream_ptr())
         return self.packed
+
+    def stream_ptr(self) -> int:
+        return self.torch.cuda.current_stream(self.device).cuda_stream or 1
 
 
 class ShardedModel:
@@ -83,6 +208,63 @@ class ShardedModel:
         self._cmd_host = None
         self._packed_host = None
         self._on_gpu = hasattr(local, "packed") and local.packed.is_cuda
+        self._peer = None
+        self._mailbox = None
+        if self.world > 1:
+            self._check_prior_placement()
+            self._setup_fast_paths()
+
+    def _check_prior_placement(self):
+        """The Gaussian prior must be enabled on exactly one rank, or it is counted ``world`` times --
+        silently: the fit still converges.  Checked once, collectively."""
+        model = getattr(self.local, "model", None)
+        if model is None or not hasattr(model, "prior_enabled"):
+            return
+        torch, dist = self.torch, self.dist
+        dev = self.local.packed.device if self._on_gpu else torch.device("cpu")
+        flag = torch.tensor([1 if model.prior_enabled else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, group=self.group)
+        if int(flag.item()) != 1:
+            raise ValueError(f"the prior is enabled on {int(flag.item())} ranks; call model.set_prior_enabled(rank == 0) "
+                             "so that it is counted exactly once")
+
+    def _setup_fast_paths(self):
+        """Peer-memory all-reduce and the shared-memory mailbox (both collective to set up).  Each falls
+        back -- on every rank together -- to its torch.distributed equivalent."""
+        import os
+
+        torch, dist = self.torch, self.dist
+        if self._on_gpu and os.environ.get("ANML_B200_COLLECTIVE", "peer").lower() != "nccl":
+            try:
+                self._peer = PeerAllReduce(self.local.packed.device.index, self.local.packed.numel(), self.group)
+            except Exception as exc:  # every rank raises together (the constructor agrees on the outcome)
+                self._peer = None
+                if self.rank == 0:
+                    import warnings
+
+                    warnings.warn(f"peer-memory all-reduce unavailable ({exc}); using dist.all_reduce")
+        if os.environ.get("ANML_B200_MAILBOX", "shm").lower() == "shm":
+            dev = self.local.packed.device if self._on_gpu else torch.device("cpu")
+            ok = torch.ones(1, dtype=torch.int32, device=dev)
+            box = None
+            try:
+                box = ShmMailbox(self.P, self.group)
+            except Exception:
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 1:
+                self._mailbox = box
+            elif box is not None:
+                box.close()
+
+    def close(self):
+        """Collective: release the peer windows and the mailbox."""
+        if self._peer is not None:
+            self._peer.close()
+            self._peer = None
+        if self._mailbox is not None:
+            self._mailbox.close()
+            self._mailbox = None
 
     # ---- collective evaluation (every rank calls this with the same x) -------------
     def evaluate_collective(self, x: np.ndarray, hessian: bool = True):
@@ -91,7 +273,10 @@ class ShardedModel:
             raise ValueError(f"x has {x.size} entries, the model has {self.P} coefficients")
         packed = self.local.eval_packed(x, hessian)
         if self.world > 1:
-            self.dist.all_reduce(packed, op=self.dist.ReduceOp.SUM, group=self.group)
+            if self._peer is not None:
+                self._peer.all_reduce(packed, self.local.stream_ptr())
+            else:
+                self.dist.all_reduce(packed, op=self.dist.ReduceOp.SUM, group=self.group)
         return packed
 
     def unpack(self, packed, hessian: bool = True):
@@ -108,6 +293,8 @@ class ShardedModel:
                 host = packed.detach().numpy()
         else:
             host = np.asarray(packed)
+        if self._peer is not None and host[0] != host[0]:
+            self._peer.check()  # NaN objective: a peer may have missed the all-reduce (timeout)
         if host[1 + P + P * P] != 0.0:
             raise ValueError("linear predictor outside the domain of a Log/Logit mapping")
         obj = float(host[0])
@@ -122,6 +309,11 @@ class ShardedModel:
         torch = self.torch
         if self.world == 1:
             return op, x
+        if self._mailbox is not None:
+            if self.rank == 0:
+                self._mailbox.post(op, x)
+                return op, (None if x is None else np.array(x, dtype=np.float64, copy=True))
+            return self._mailbox.wait()
         dev = self.local.packed.device if hasattr(self.local, "packed") else torch.device("cpu")
         if self._cmd is None:
             self._cmd = torch.zeros(1 + self.P, dtype=torch.float64, device=dev)
@@ -152,14 +344,19 @@ class ShardedModel:
         self.num_evaluations += 1
         return out
 
+    # trust-constr asks for objective, gradient and Hessian at the same x back to back, so by default the
+    # first call pays for the full evaluation and the other two hit the cache.  With eager_hessian = False
+    # objective / gradient take the gradient-only (HBM-bound) pass unless a Hessian evaluation is cached.
+    eager_hessian = True
+
     def objective(self, x) -> float:
-        return self.evaluate(x)[0]
+        return self.evaluate(x, hessian=self.eager_hessian)[0]
 
     def gradient(self, x) -> np.ndarray:
-        return self.evaluate(x)[1].copy()
+        return self.evaluate(x, hessian=self.eager_hessian)[1].copy()
 
     def hessian(self, x) -> np.ndarray:
-        return self.evaluate(x)[2].copy()
+        return self.evaluate(x, hessian=True)[2].copy()
 
     def serve(self) -> int:
         """Ranks != 0: evaluate on request until rank 0 calls ``stop()``."""

@@ -146,7 +146,11 @@ class Parameter:
         for v in self.variables:
             if type(v) is not Variable and not getattr(v, "_resolves_on_device", False):
                 v.attach(df)
-        design = _native.Design(n, self.size, self.device)
+        # A parameter that is exactly one spline variable gets a *deferred* design: the basis block is only
+        # recorded, and the dense (n, nb) matrix is built if and when something reads it (design_mat,
+        # get_params, a dense evaluation).  A model on the banded evaluator never does (BASELINE config #3).
+        lone_spline = len(self.variables) == 1 and getattr(self.variables[0], "_resolves_on_device", False)
+        design = _native.Design(n, self.size, self.device, deferred=lone_spline)
         col = 0
         checks = []
         for v in self.variables:

@@ -79,9 +79,7 @@ class SplineVariable(Variable):
 
         self.component.attach(df)
         x = _native.as_f64(self.component.value, self.component.key)
-        if self.device_abscissae is not None:
-            self.device_abscissae.free()
-            self.device_abscissae = None
+        self.device_abscissae = None  # (a deferred design of the previous attach may still borrow the old copy)
         xbuf = _native.DeviceBuffer(design.device, x)
         try:
             if isinstance(self.spline, SplineGetter):
@@ -96,7 +94,7 @@ class SplineVariable(Variable):
             if sp.num_spline_bases != self.size:
                 raise NotImplementedError("ldegree/rdegree that change the basis count are not supported")
             self.last_interval_index = design.set_spline(col0, None, sp.knots, sp.degree, sp.ldegree or 0, sp.rdegree or 0, 0,
-                                                         want_index=False, x_dev_ptr=xbuf.ptr)
+                                                         want_index=False, x_dev_ptr=xbuf.ptr, keepalive=xbuf)
         except BaseException:
             xbuf.free()
             raise

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ANML_B200_VERSION 100 /* 0.1.0 */
+#define ANML_B200_VERSION 200 /* 0.2.0 */
 
 /* status codes */
 enum {
@@ -72,11 +72,22 @@ int anml_dev_alloc(int device, int64_t bytes, void** out_dev);
 int anml_dev_free(int device, void* dev);
 int anml_dev_upload(int device, void* dst_dev, const void* src_host, int64_t bytes);
 int anml_dev_download(int device, void* dst_host, const void* src_dev, int64_t bytes);
+/* free the pinned / device staging lanes the uploads of `device` keep between calls (device < 0: every
+ * device); they are rebuilt on demand */
+int anml_upload_release(int device);
 
 /* ---- design matrix: replaces Parameter.design_mat = np.hstack([...])
  *      (src/anml/parameter/main.py:160-162) with a row-major (n, p) FP64
  *      matrix resident in HBM, leading dimension rounded up to even -------- */
 int anml_design_create(int device, int64_t n_rows, int n_cols, anml_design** out);
+/* Same shape contract, but nothing is allocated yet: spline blocks set with device-resident abscissae
+ * (anml_design_set_spline, x_on_device = 1, interval_out = NULL) are only RECORDED -- the abscissae are
+ * borrowed and must outlive the design -- and the dense matrix is built the first time something needs
+ * it (set_columns, download, params, shape(dev), validate, or an evaluation that streams it).  A
+ * one-spline model on the banded evaluator (anml_model_enable_banded_spline) never does: BASELINE
+ * config #3 then holds the 0.4 GB of abscissae instead of an 8.8 GB design it does not read. */
+int anml_design_create_deferred(int device, int64_t n_rows, int n_cols, anml_design** out);
+int anml_design_is_materialized(const anml_design* d, int* out);
 /* adopt a caller-owned device matrix without copying (ld even, 16-byte aligned) */
 int anml_design_wrap_device(int device, int64_t n_rows, int n_cols, double* dev, int64_t ld, anml_design** out);
 int anml_design_destroy(anml_design* d);
@@ -151,10 +162,34 @@ int anml_model_eval(anml_model* m, const double* x_host, int want, double* obj, 
  * stream) without synchronising: the row-sharded caller all-reduces it over
  * NCCL before reading it. */
 int anml_model_eval_async(anml_model* m, const double* x_host, int want, double* packed_dev, void* stream);
+/* Ordering: an evaluation queued with anml_model_eval_async on a caller's stream is followed by an
+ * event; the setters, anml_model_eval and anml_model_destroy wait for it, and an evaluation on a
+ * different stream is ordered behind it on the device. */
 /* CUDA-event time of the dominant kernel, accumulated over evaluations since
  * the last reset (what bench.py reports as roofline.achieved) */
 int anml_model_kernel_time(anml_model* m, int reset, double* total_ms, int64_t* launches, int64_t* all_launches);
 int anml_model_set_option(anml_model* m, const char* name, int64_t value);
+
+/* ---- row-sharded evaluation: all-reduce of the packed record over peer memory ----
+ * The reference has no distributed layer; this is the exchange step the north star names ("only the
+ * p-vector gradient and the p x p Hessian all-reduced over NVLink").  One process per GPU of one node.
+ * Each rank creates a window (cudaMalloc), exports its cudaIpcMemHandle (anml_comm_handle_bytes bytes),
+ * the host layer gathers the handles of all ranks in rank order (any transport: torch.distributed,
+ * MPI, a file) and hands them to anml_comm_connect, then synchronises the ranks once.  After that
+ *   anml_comm_allreduce_async(c, buf, n, stream)
+ * sums buf (device, n <= max_elems doubles) over the ranks in place with ONE kernel launch on `stream`
+ * (a cudaStream_t; NULL or cudaStreamLegacy = the legacy default stream): peers' records are read
+ * through NVLink in rank order, so every rank gets the same bits.  Every rank must call it the same
+ * number of times.  anml_comm_error reports the evaluation number at which a peer failed to arrive
+ * within the timeout (ANML_B200_COMM_TIMEOUT_S, default 20 s; the record is then NaN), 0 if none. */
+typedef struct anml_comm anml_comm;
+int anml_comm_handle_bytes(int* out);
+int anml_comm_create(int device, int rank, int world, int64_t max_elems, anml_comm** out);
+int anml_comm_export(anml_comm* c, void* handle_out);
+int anml_comm_connect(anml_comm* c, const void* all_handles);
+int anml_comm_allreduce_async(anml_comm* c, double* buf_dev, int64_t n_elems, void* stream);
+int anml_comm_error(anml_comm* c, int64_t* failed_epoch);
+int anml_comm_destroy(anml_comm* c);
 
 #ifdef __cplusplus
 }

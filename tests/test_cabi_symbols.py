@@ -29,7 +29,7 @@ def test_binding_covers_every_declared_symbol():
 
 def test_version_and_error_string():
     lib = _native.load()
-    assert lib.anml_version() == 100
+    assert lib.anml_version() == 200
     n = ctypes.c_int(-1)
     rc = lib.anml_device_count(ctypes.byref(n))
     assert rc in (_native.OK, _native.ECUDA)
@@ -74,4 +74,4 @@ def test_plain_c_program_links_and_runs(tmp_path):
     assert res.returncode == 0, res.stderr
     run = subprocess.run([str(exe)], capture_output=True, text=True)
     assert run.returncode == 0, run.stdout + run.stderr
-    assert "version=100" in run.stdout
+    assert "version=200" in run.stdout

@@ -33,6 +33,9 @@ class OracleShard:
         self.num_coefs = X.shape[1]
         self.packed_size = 2 + self.num_coefs + self.num_coefs**2
         self.priors = [{"direct": (np.zeros(self.num_coefs), np.full(self.num_coefs, prior_sd))}] if with_prior else None
+        from types import SimpleNamespace
+
+        self.model = SimpleNamespace(prior_enabled=with_prior)  # what ShardedModel's prior-placement check reads
 
     def eval_packed(self, x, want_hessian):
         o, g, h = O.model_eval_fused("binomial", self.obs, [self.X], ["expit"], x, priors=self.priors)
@@ -49,16 +52,25 @@ def _problem():
     return X, obs, beta
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, mailbox="shm"):
     import torch.distributed as dist
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["ANML_B200_MAILBOX"] = mailbox
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         X, obs, beta = _problem()
         lo, hi = shard_rows(X.shape[0], world, rank)
+        # a prior enabled on every rank would be counted world times: refused at construction
+        try:
+            ShardedModel(OracleShard(X[lo:hi], obs[lo:hi], 2.0, with_prior=True))
+            raise AssertionError("prior on every rank was accepted")
+        except ValueError as e:
+            assert "exactly once" in str(e)
         model = ShardedModel(OracleShard(X[lo:hi], obs[lo:hi], 2.0, with_prior=(rank == 0)))
+        assert (model._mailbox is not None) == (mailbox == "shm")  # host shared-memory command channel
+        assert model._peer is None                                  # peer memory needs GPUs
         x = 0.5 * beta
         # collective call: every rank gets the full-sum result
         o, g, h = model.unpack(model.evaluate_collective(x, True))
@@ -80,13 +92,15 @@ def _worker(rank, world, port, out):
         else:
             assert res is None
             out.put(("ok", 0))
+        model.close()
     except Exception as e:  # pragma: no cover
         out.put(("fail", repr(e)))
     finally:
         dist.destroy_process_group()
 
 
-def test_two_rank_gloo_sharded_fit():
+@pytest.mark.parametrize("mailbox", ["shm", "broadcast"])
+def test_two_rank_gloo_sharded_fit(mailbox):
     import torch.multiprocessing as mp
 
     with socket.socket() as s:
@@ -94,7 +108,7 @@ def test_two_rank_gloo_sharded_fit():
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out, mailbox)) for r in range(2)]
     for p in procs:
         p.start()
     results = [out.get(timeout=240) for _ in procs]
