@@ -54,3 +54,22 @@ print(json.dumps({"banded_enabled": bool(ok), "enable_ms": t_en * 1e3, "banded_e
                   "obj_rel_diff": abs(ob - o) / abs(o), "grad_rel_diff": float(np.abs(gb - gr).max() / np.abs(gr).max()),
                   "hess_rel_diff": float(np.abs(Hb - H).max() / np.abs(H).max()), "hess_sym": bool(np.array_equal(Hb, Hb.T)),
                   "algorithmic_GBps": n * 3 * 8 / (kms_b / 10) / 1e6}))
+
+# BASELINE config #3 proper: default obs_se (not read), x and obs only -> 16 bytes per row
+m2 = N.NativeModel(n, "gaussian", 1)
+m2.set_param(0, d, N.LINK_CODES["Identity"])
+m2.set_obs(dev_ptr=obs.data_ptr(), keepalive=obs)
+ok2 = m2.enable_banded_spline(knots, deg, x_dev_ptr=xs.data_ptr())
+for _ in range(3): m2.eval(x)
+m2.kernel_time(reset=True)
+t0 = time.perf_counter()
+for _ in range(20): o2, g2, H2 = m2.eval(x)
+e2e_2 = (time.perf_counter() - t0) / 20 * 1e3
+kms_2, _, _ = m2.kernel_time(reset=True)
+m2.kernel_time(reset=True)
+for _ in range(20): m2.eval(x, N.WANT_OBJ | N.WANT_GRAD)
+kms_2g, _, _ = m2.kernel_time(reset=True)
+print(json.dumps({"plain_banded_enabled": bool(ok2), "eval_ms": e2e_2, "kernel_ms": kms_2 / 20, "objgrad_kernel_ms": kms_2g / 20,
+                  "algorithmic_GBps": n * 2 * 8 / (kms_2 / 20) / 1e6, "obj_rel_diff_vs_dense": abs(o2 - o) / abs(o),
+                  "grad_rel_diff_vs_dense": float(np.abs(g2 - gr).max() / np.abs(gr).max()),
+                  "hess_rel_diff_vs_dense": float(np.abs(H2 - H).max() / np.abs(H).max())}))
