@@ -66,6 +66,7 @@ SIGNATURES = {
     "anml_model_eval": (C.c_int, [C.c_void_p, _c_double_p, C.c_int, _c_double_p, _c_double_p, _c_double_p]),
     "anml_model_eval_async": (C.c_int, [C.c_void_p, _c_double_p, C.c_int, C.c_void_p, C.c_void_p]),
     "anml_model_kernel_time": (C.c_int, [C.c_void_p, C.c_int, _c_double_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "anml_model_main_kernel": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "anml_model_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "anml_comm_handle_bytes": (C.c_int, [C.POINTER(C.c_int)]),
     "anml_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
@@ -194,6 +195,7 @@ class Design:
         """Adopt a caller-owned device matrix (e.g. a torch CUDA tensor) without copying."""
         d = cls(n_rows, n_cols, device, _wrap=(int(dev_ptr), int(ld)))
         d._keepalive = keepalive
+        d.wrapped = (int(dev_ptr), int(n_rows), int(n_cols), int(ld), device)  # identity of the borrowed matrix
         return d
 
     def set_columns(self, col0: int, block: np.ndarray):
@@ -484,6 +486,11 @@ class NativeModel:
         ms, n, a = C.c_double(0.0), C.c_int64(0), C.c_int64(0)
         check(load().anml_model_kernel_time(self.handle, 1 if reset else 0, C.byref(ms), C.byref(n), C.byref(a)))
         return ms.value, n.value, a.value
+
+    def main_kernel(self) -> str:
+        buf = C.create_string_buffer(200)
+        check(load().anml_model_main_kernel(self.handle, buf, 200))
+        return buf.value.decode()
 
     def free(self):
         if getattr(self, "handle", None) is not None and _lib is not None:

@@ -132,7 +132,13 @@ class Model:
             code = p.transform.device_code
             if code < 0:
                 raise NotImplementedError(f"{p.transform!r} has no device implementation")
-            nm.set_param(k, p.device_design, code, p.device_offset)
+            design = p.device_design
+            # two parameters that wrap the SAME device matrix (Parameter.attach_device) are one design to the
+            # library: the mean / variance model then takes the shared-design path (X read three times)
+            first = self.parameters[0].device_design
+            if k > 0 and getattr(design, "wrapped", None) is not None and getattr(first, "wrapped", None) == design.wrapped:
+                design = first
+            nm.set_param(k, design, code, p.device_offset)
         if obs_ptr is not None:
             nm.set_obs(dev_ptr=obs_ptr, keepalive=keepalive)
             if se_ptr is not None:

@@ -168,6 +168,9 @@ int anml_model_eval_async(anml_model* m, const double* x_host, int want, double*
 /* CUDA-event time of the dominant kernel, accumulated over evaluations since
  * the last reset (what bench.py reports as roofline.achieved) */
 int anml_model_kernel_time(anml_model* m, int reset, double* total_ms, int64_t* launches, int64_t* all_launches);
+/* name and template arguments of the kernel that anml_model_kernel_time last timed, e.g.
+ * "fused_hess_kernel<4, 2, 0, 0, 1, 32>" (bench.py looks its ncu DRAM traffic up under that key) */
+int anml_model_main_kernel(const anml_model* m, char* out, int out_len);
 int anml_model_set_option(anml_model* m, const char* name, int64_t value);
 
 /* ---- row-sharded evaluation: all-reduce of the packed record over peer memory ----

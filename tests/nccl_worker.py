@@ -50,10 +50,29 @@ def main():
         model.attach(df)
         model.set_prior_enabled(rank == 0)  # the prior is counted once
         sharded = ShardedModel(NativeLocalEvaluator(model, torch.device("cuda", local_rank)))
+        # the product path: one peer-memory kernel per evaluation (csrc/comm.cuh), x through the host mailbox
+        assert sharded._peer is not None, "peer-memory all-reduce was not set up"
+        assert sharded._mailbox is not None
 
         priors = [{"direct": (np.zeros(p), np.full(p, 2.0))}]
         x = 0.5 * beta
         o, g, h = sharded.unpack(sharded.evaluate_collective(x, True))
+        # the same evaluation with NCCL doing the sum: same numbers to summation order
+        os.environ["ANML_B200_COLLECTIVE"] = "nccl"
+        via_nccl = ShardedModel(NativeLocalEvaluator(model, torch.device("cuda", local_rank)))
+        os.environ["ANML_B200_COLLECTIVE"] = "peer"
+        assert via_nccl._peer is None
+        o2, g2, h2 = via_nccl.unpack(via_nccl.evaluate_collective(x, True))
+        assert abs(o2 - o) <= 1e-13 * abs(o) and np.abs(g2 - g).max() <= 1e-13 * np.abs(g).max()
+        assert np.abs(h2 - h).max() <= 1e-13 * np.abs(h).max()
+        via_nccl.close()
+        # many evaluations back to back (the two data buffers of the window alternate), gradient-only too
+        for k in range(40):
+            ok_, gk, hk = sharded.unpack(sharded.evaluate_collective(x * (1.0 + 1e-3 * k), k % 3 != 0), k % 3 != 0)
+            wk = O.model_eval_fused("binomial", obs, [X], ["expit"], x * (1.0 + 1e-3 * k), priors=priors)
+            assert abs(ok_ - wk[0]) <= 1e-10 * abs(wk[0]) and np.abs(gk - wk[1]).max() <= 1e-10 * np.abs(wk[1]).max()
+            if hk is not None:
+                assert np.abs(hk - wk[2]).max() <= 1e-9 * np.abs(wk[2]).max()
         want = O.model_eval_fused("binomial", obs, [X], ["expit"], x, priors=priors)
         assert abs(o - want[0]) <= 1e-10 * abs(want[0]), (o, want[0])
         assert np.abs(g - want[1]).max() <= 1e-10 * np.abs(want[1]).max()
@@ -84,6 +103,7 @@ def main():
             smodel = Model("gaussian", DataExample("obs", "obs_se"), [spar], device=local_rank)
             smodel.attach(sdf)
             assert smodel.banded_spline is True
+            assert not spar.device_design.materialized  # the dense design of a banded model is never built
             ssh = ShardedModel(NativeLocalEvaluator(smodel, torch.device("cuda", local_rank)))
             bx = np.linspace(-1.0, 1.0, spar.size)
             so, sg, sh = ssh.unpack(ssh.evaluate_collective(bx, True))
@@ -92,6 +112,7 @@ def main():
             assert abs(so - sw[0]) <= 1e-10 * abs(sw[0])
             assert np.abs(sg - sw[1]).max() <= 1e-10 * np.abs(sw[1]).max()
             assert np.abs(sh - sw[2]).max() <= 1e-9 * np.abs(sw[2]).max()
+            ssh.close()
 
         res = sharded.fit(np.zeros(p), options={"gtol": 1e-10})
         if rank == 0:
@@ -105,6 +126,7 @@ def main():
             print(f"NCCL_SHARDED_OK world={world} evals={sharded.num_evaluations} coef_err={err:.2e}", flush=True)
         else:
             assert res is None
+        sharded.close()
     finally:
         dist.destroy_process_group()
 

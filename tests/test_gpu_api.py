@@ -392,3 +392,26 @@ def test_attach_from_pyarrow_table_equals_attach_from_pandas():
     a, b = model_pd.evaluate(x), model_pa.evaluate(x)
     assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     np.testing.assert_array_equal(par_pa.get_params(x, table), par_pd.get_params(x))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("link", ["log", "logit", "exp", "expit", "identity"])
+def test_device_link_values_match_the_reference_grid(golden, link):
+    """SmoothMapping values of every order computed ON THE DEVICE (Parameter.get_params through a one-column
+    design whose linear predictor is the grid itself) against the imported reference's outputs on the same grid
+    (tests/golden: link/<name>/order{0,1,2}; smoothmapping.py:59-156).  Rows a4-a7 of SURVEY.md section 8."""
+    from anml_b200 import parameter as P
+    from anml_b200.variable import Variable
+
+    grid = np.ascontiguousarray(golden[f"link/{link}/x"], dtype=np.float64)
+    par = P.Parameter([Variable("v")], transform=getattr(P, LINKS[link])())
+    par.attach(pd.DataFrame({"v": grid}))
+    for order in (0, 1, 2):
+        want = golden[f"link/{link}/order{order}"]
+        got = par.get_params(np.ones(1), order=order)
+        if order == 1:
+            got, want = got[:, 0], want * grid             # J = f'(y) * x, one column
+        elif order == 2:
+            got, want = got[:, 0, 0], want * (grid * grid)  # T = f''(y) * x x^T
+        # libdevice and NumPy's libm each round exp / log to within an ulp or two; products add a few more
+        np.testing.assert_allclose(got, want, rtol=4e-15, atol=1e-300)

@@ -272,3 +272,27 @@ def test_logistic_objective_product_accumulator_extremes():
     Xn[7, 2] = np.nan
     got = gpu_eval("binomial", Xn, obs[:1000], None, None, "expit", x)
     assert np.isnan(got[0])
+
+
+# ---- Log / Logit mappings on the device: VALUES against the reference (SURVEY.md row a7,
+# src/anml/parameter/smoothmapping.py:96-104, :146-156), not only the domain errors
+@pytest.mark.parametrize("link", ["log", "logit"])
+@pytest.mark.parametrize("general", [0, 1])
+def test_log_and_logit_links_in_a_model(link, general):
+    rng = np.random.default_rng(17)
+    n, p = 4003, 6
+    X = np.abs(rng.normal(size=(n, p))) + 0.05
+    X[:, 0] = 1.0
+    beta = np.abs(rng.normal(size=p)) * 0.2 + 0.05
+    if link == "logit":  # keep the linear predictor strictly inside (0, 1)
+        scale = 0.9 / (X @ beta).max()
+        beta = beta * scale
+    y = X @ beta
+    assert (y > 0).all() and (link == "log" or (y < 1).all())
+    obs = O.link_eval(link, y) + 0.1 * rng.normal(size=n)
+    se = rng.uniform(0.5, 1.5, size=n)
+    want = O.model_eval_fused("gaussian", obs, [X], [link], beta, obs_se=se)
+    got = gpu_eval("gaussian", X, obs, se, None, link, beta, options=(("force_generic", general),))
+    check(got, want)
+    with pytest.raises(ValueError):  # outside the domain: the reference raises before computing (:98-99, :148-151)
+        gpu_eval("gaussian", X, obs, se, None, link, -beta, options=(("force_generic", general),))
