@@ -1159,7 +1159,7 @@ static int launch_hess_tt(const anml_design* d, const FusedArgs& a, int grid, cu
         configured.set(d->device);
     }
     const CUtensorMap& tm = ROWS == 64 ? (TMA3D ? d->tmap3d64 : d->tmap64) : (TMA3D ? d->tmap3d : d->tmap32);
-    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tm, a);
+    kern<<<grid, C::LAUNCH_THREADS, C::SMEM_BYTES, st>>>(tm, a);
     CU_TRY(cudaGetLastError());
     snprintf(g_kernel, sizeof(g_kernel), "fused_hess_kernel<%d, %d, %d, %d, %d, %d>", NB16, NHELP, SIGNED ? 1 : 0, MODE, TMA3D ? 1 : 0, ROWS);
     return ANML_OK;

@@ -31,9 +31,13 @@ __device__ __forceinline__ LinkVal link_eval(int link, double y) {
             break;
         }
         case LINK_EXPIT: {  // :119-126
+            // the reference's expressions with the reference's overflow structure: z / (1+z)**2 and
+            // z (z-1) / (z+1)**3 are 0 once the denominator overflows and nan once the numerator does
+            // too (y < -355 resp. -709.78) -- multiplying by 1/(1+z) instead would return tiny values or inf
+            // at those arguments
             const double z = exp(-y);
-            const double q = 1.0 / (1.0 + z);
-            v.f = q; v.d1 = z * q * q; v.d2 = z * (z - 1.0) * q * q * q;
+            const double s = 1.0 + z;
+            v.f = 1.0 / s; v.d1 = z / (s * s); v.d2 = z * (z - 1.0) / (s * s * s);
             break;
         }
         case LINK_LOGIT: {  // :146-156, domain :148-151
