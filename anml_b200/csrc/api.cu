@@ -1159,7 +1159,7 @@ static int launch_hess_tt(const anml_design* d, const FusedArgs& a, int grid, cu
         configured.set(d->device);
     }
     const CUtensorMap& tm = ROWS == 64 ? (TMA3D ? d->tmap3d64 : d->tmap64) : (TMA3D ? d->tmap3d : d->tmap32);
-    kern<<<grid, C::LAUNCH_THREADS, C::SMEM_BYTES, st>>>(tm, a);
+    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tm, a);
     CU_TRY(cudaGetLastError());
     snprintf(g_kernel, sizeof(g_kernel), "fused_hess_kernel<%d, %d, %d, %d, %d, %d>", NB16, NHELP, SIGNED ? 1 : 0, MODE, TMA3D ? 1 : 0, ROWS);
     return ANML_OK;
@@ -1246,7 +1246,7 @@ static int run_dual_terms(anml_model* m, double* packed, cudaStream_t st) {
     if (grid < 1) grid = 1;
     FusedArgs a;
     memset(&a, 0, sizeof(a));
-    a.n = m->n; a.p = d->p; a.link = m->par[0].link; a.link1 = m->par[1].link; a.family = m->family;
+    a.n = m->n; a.p = d->p; a.link = m->par[0].link; a.link1 = m->par[1].link; a.family = m->family; a.fast = m->no_fast ? 0 : 1;
     a.beta = m->d_beta + m->par[0].pad_off; a.beta1 = m->d_beta + m->par[1].pad_off;
     a.obs = m->obs; a.offset = m->par[0].offset; a.offset1 = m->par[1].offset; a.weights = m->weights;
     a.out_r0 = m->vec[2]; a.out_r1 = m->vec[3]; a.out_w00 = m->vec[4]; a.out_w01 = m->vec[5]; a.out_w11 = m->vec[6];
@@ -1289,12 +1289,19 @@ static int run_fused_block(anml_model* m, const anml_design* d, FusedArgs a, boo
         break;
     if (specialised) {
         const bool sgn = !weights_positive(a.family, a.link, a.fast != 0) || m->force_signed;
+// helper warps per team: 2 at full width (registers: setmaxnreg 216 / 144); narrow designs are paced by
+// the helpers' per-row work, not by the tensor warp, and their accumulators are few: more helpers there
+#ifndef ANML_NARROW_NHELP
+#define ANML_NARROW_NHELP 2
+#endif
 #define HESS_CASE(NB)                                                                              \
-    case NB:                                                                                       \
-        if (mode == 3) rc = launch_hess_t<NB, 2, true, 3>(d, a, grid, st);                         \
-        else if (mode == 1) rc = launch_hess_t<NB, 2, true, 1>(d, a, grid, st);                    \
-        else rc = sgn ? launch_hess_t<NB, 2, true, 0>(d, a, grid, st) : launch_hess_t<NB, 2, false, 0>(d, a, grid, st); \
-        break;
+    case NB: {                                                                                     \
+        constexpr int NH = (NB <= 2) ? ANML_NARROW_NHELP : 2;                                      \
+        if (mode == 3) rc = launch_hess_t<NB, NH, true, 3>(d, a, grid, st);                        \
+        else if (mode == 1) rc = launch_hess_t<NB, NH, true, 1>(d, a, grid, st);                   \
+        else rc = sgn ? launch_hess_t<NB, NH, true, 0>(d, a, grid, st) : launch_hess_t<NB, NH, false, 0>(d, a, grid, st); \
+        break;                                                                                     \
+    }
         switch (nb16) {
             HESS_CASE(1)
             HESS_CASE(2)
@@ -1638,7 +1645,7 @@ static int eval_general(anml_model* m, int want, double* packed, cudaStream_t st
         if (hess && !m->no_specialise) {
             FusedArgs a;
             memset(&a, 0, sizeof(a));
-            a.n = m->n; a.p = d->p; a.link = m->par[0].link; a.link1 = m->par[1].link; a.family = m->family;
+            a.n = m->n; a.p = d->p; a.link = m->par[0].link; a.link1 = m->par[1].link; a.family = m->family; a.fast = m->no_fast ? 0 : 1;
             a.beta = m->d_beta + m->par[0].pad_off; a.beta1 = m->d_beta + m->par[1].pad_off;
             a.obs = m->obs; a.offset = m->par[0].offset; a.offset1 = m->par[1].offset; a.weights = m->weights;
             a.out_r1 = m->vec[3]; a.out_w01 = m->vec[5]; a.out_w11 = m->vec[6];

@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256, 1) fused_eval_kernel(const __grid_constan
             if (valid) {
                 if (a.offset) y0 += a.offset[row];
                 if (a.offset1) y1 += a.offset1[row];
-                const RowTerms2 rt = row_terms2(a.link, a.link1, y0, y1, a.obs[row]);
+                const RowTerms2 rt = row_terms2(a.link, a.link1, y0, y1, a.obs[row], a.fast != 0);
                 const double wt = a.weights ? a.weights[row] : 1.0;
                 objacc += wt * rt.l;
                 a.out_r0[row] = wt * rt.r0;

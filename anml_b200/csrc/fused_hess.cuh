@@ -55,17 +55,9 @@ struct HessCfg {
     static constexpr int TEAMS = 4;
     static constexpr int HELPERS = NHELP;  // per team
     static constexpr int WARPS = TEAMS * (1 + HELPERS);
-    static constexpr int THREADS = WARPS * 32;  // tensor warps + helpers (the named barrier of the epilogue counts these)
-#ifdef ANML_HESS_PRODUCER
-    // + a TMA producer warpgroup (setmaxnreg is a warpgroup-wide instruction: one producing warp, three idle
-    // ones): 512 threads x 128 registers at launch; afterwards 128*216 (tensor) + 256*136 (helpers) + 128*24 = 65536
-    static constexpr int LAUNCH_THREADS = THREADS + 128;
-    static constexpr int REGS_M = 216, REGS_H = 136, REGS_P = 24;
-#else
-    static constexpr int LAUNCH_THREADS = THREADS;
+    static constexpr int THREADS = WARPS * 32;
     // 384 threads x 168 registers at launch = 4*32*216 (tensor warps) + 8*32*144 (helpers)
     static constexpr int REGS_M = 216, REGS_H = 144;
-#endif
     static constexpr int NB8 = 2 * NB16;
     static constexpr int NT = NB8 * (NB8 + 1) / 2;
     static constexpr int HALVES = ROWS / 32;
@@ -75,7 +67,7 @@ struct HessCfg {
     static constexpr int NBUF = (49152 / BUF_BYTES) > 8 ? 8 : (49152 / BUF_BYTES);
     static constexpr int TEAM_BYTES = NBUF * BUF_BYTES;
     static constexpr int EL = (2 * NT + NB8 + 1) * 32;
-    static constexpr int SMEM_BYTES = 1024 + TEAMS * TEAM_BYTES + TEAMS * NBUF * ROWS * 4 /*sign masks*/ + TEAMS * NBUF * 3 * 8 /*full barriers, ready flags, empty barriers*/ +
+    static constexpr int SMEM_BYTES = 1024 + TEAMS * TEAM_BYTES + TEAMS * NBUF * ROWS * 4 /*sign masks*/ + TEAMS * NBUF * 2 * 8 /*full barriers, ready flags*/ +
                                       2 * 16 * NB16 * 8 /*beta, beta1*/ + TEAMS * HELPERS * (NB8 + 1) * 32 * 8 /*helper g, obj; transpose scratch*/ +
                                       TEAMS * HELPERS * 64 * 8 /*helper r, sqrt|w|*/;
 };
@@ -143,7 +135,7 @@ __device__ __forceinline__ void mma_kstep(double* acc, const double* av, uint32_
 // TMA3D: the tensor map is the 3-D view (16 cols, rows, column groups) and one instruction
 // fetches the whole block (api.cu encodes it when p is a multiple of 16).
 template <int NB16, int NHELP, bool SIGNED, int MODE, bool TMA3D, int ROWS>
-__global__ void __launch_bounds__(HessCfg<NB16, NHELP, ROWS>::LAUNCH_THREADS, 1) fused_hess_kernel(const __grid_constant__ CUtensorMap tmap32, const FusedArgs a) {
+__global__ void __launch_bounds__(128 * (1 + NHELP), 1) fused_hess_kernel(const __grid_constant__ CUtensorMap tmap32, const FusedArgs a) {
     using C = HessCfg<NB16, NHELP, ROWS>;
     constexpr int KSTEPS = C::KSTEPS, GB = C::GROUP_BYTES, SIGN_BYTES = ROWS * 4;
     constexpr int NB8 = C::NB8, NT = C::NT, NBUF = C::NBUF, TEAMS = C::TEAMS;
@@ -154,22 +146,20 @@ __global__ void __launch_bounds__(HessCfg<NB16, NHELP, ROWS>::LAUNCH_THREADS, 1)
     // layout: rings | sign masks | barriers | beta | helper records (gradient rows, objective row)
     const uint32_t signs_base = smem_base + TEAMS * C::TEAM_BYTES;
     const uint32_t bars_base = signs_base + TEAMS * NBUF * SIGN_BYTES;
-    const uint32_t empty_base = bars_base + TEAMS * NBUF * 2 * 8;  // empty[team][buf] (producer-warp variant)
-    const uint32_t beta_base = empty_base + TEAMS * NBUF * 8;
+    const uint32_t beta_base = bars_base + TEAMS * NBUF * 2 * 8;
     const uint32_t hrec_base = beta_base + 2 * 16 * NB16 * 8;  // [beta | beta1 (MODE 3)]
     const uint32_t hterm_base = hrec_base + TEAMS * C::HELPERS * (NB8 + 1) * 256;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int team = warp & 3;
-    const int role = warp >> 2;  // 0 = tensor warp, 1.. = helpers, 1 + NHELP = TMA producer (ANML_HESS_PRODUCER)
+    const int role = warp >> 2;  // 0 = tensor warp, 1.. = helpers
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap32);
         for (int q = 0; q < TEAMS; ++q)
             for (int i = 0; i < NBUF; ++i) {
                 mbar_init(bars_base + (q * NBUF * 2 + i) * 8, 1);
-                mbar_init(empty_base + (q * NBUF + i) * 8, 32);
                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(bars_base + (q * NBUF * 2 + NBUF + i) * 8), "r"(0) : "memory");
             }
         mbar_fence_init();
@@ -186,51 +176,6 @@ __global__ void __launch_bounds__(HessCfg<NB16, NHELP, ROWS>::LAUNCH_THREADS, 1)
     const uint32_t rdy_u32 = full_u32 + NBUF * 8;                       // ready[b] : u32 sequence flag, block rescaled + signs published
 
     const long long nblk = (a.n + ROWS - 1) / ROWS;
-#ifdef ANML_HESS_PRODUCER
-    if (role == 1 + NHELP) {
-        // ============================ TMA producer warp ============================
-        // One lane keeps the four teams' rings full: a buffer is re-armed as soon as the team's tensor warp has
-        // pulled the block into registers (empty[team][buf], 32 arrivals).  The tensor warps thereby lose the
-        // fence + expect_tx + UTMALDG sequence (behind ptxas' elect/uniform-register code) at every block boundary.
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_P));
-        if (warp == TEAMS * (1 + NHELP) && lane == 0) {
-            const int GPp = (int)gridDim.x * TEAMS;  // (block counts fit an int: at most 2^31 rows per device)
-            int nm[TEAMS], nxt[TEAMS];
-            int left = 0;
-#pragma unroll
-            for (int q = 0; q < TEAMS; ++q) {
-                const int gq = (int)blockIdx.x * TEAMS + q;
-                nm[q] = ((int)nblk > gq) ? ((int)nblk - gq + GPp - 1) / GPp : 0;
-                nxt[q] = 0;
-                left += nm[q];
-            }
-            while (left > 0) {
-#pragma unroll
-                for (int q = 0; q < TEAMS; ++q) {
-                    if (nxt[q] >= nm[q]) continue;
-                    const int b = nxt[q] % NBUF;
-                    const int use = nxt[q] / NBUF;
-                    if (use > 0 && !mbar_try(empty_base + (q * NBUF + b) * 8, (uint32_t)((use - 1) & 1))) continue;
-                    if (use > 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // helper's in-place stores before the refill
-                    const long long row0 = ((long long)blockIdx.x * TEAMS + q + (long long)nxt[q] * GPp) * ROWS;
-                    const uint32_t bar = bars_base + (q * NBUF * 2 + b) * 8;
-                    const uint32_t dst = smem_base + q * C::TEAM_BYTES + b * C::BUF_BYTES;
-                    mbar_arrive_expect_tx(bar, C::BUF_BYTES);
-                    if (TMA3D) {
-                        tma_load_3d(dst, &tmap32, 0, (int)row0, 0, bar);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < NB16; ++j) tma_load_2d(dst + j * GB, &tmap32, 16 * j, (int)row0, bar);
-                    }
-                    ++nxt[q];
-                    --left;
-                }
-            }
-        }
-        __syncthreads();  // the CTA-wide barrier before the partial record is written
-        return;
-    }
-#endif
     const long long gp = (long long)blockIdx.x * TEAMS + team;
     const long long GP = (long long)gridDim.x * TEAMS;
     const long long nmine = (nblk > gp) ? (nblk - gp + GP - 1) / GP : 0;
@@ -253,15 +198,10 @@ __global__ void __launch_bounds__(HessCfg<NB16, NHELP, ROWS>::LAUNCH_THREADS, 1)
                 for (int j = 0; j < NB16; ++j) tma_load_2d(dst + j * GB, &tmap32, 16 * j, (int)row0, bar);
             }
         };
-#ifndef ANML_HESS_PRODUCER
         if (lane == 0) {
             const int pre = nmine < NBUF ? (int)nmine : NBUF;
             for (int i = 0; i < pre; ++i) issue(i, i);
         }
-#else
-        (void)issue;
-        const uint32_t empty_u32 = empty_base + team * NBUF * 8;
-#endif
         double acc[2 * NT];
 #pragma unroll
         for (int i = 0; i < 2 * NT; ++i) acc[i] = 0.0;
@@ -304,15 +244,11 @@ __global__ void __launch_bounds__(HessCfg<NB16, NHELP, ROWS>::LAUNCH_THREADS, 1)
                     if (SIGNED) sgA = lds32(sb + (4 * (s + 2) + t) * 4);
                 } else {
                     // this block now lives entirely in registers: hand its buffer back to TMA
-#ifdef ANML_HESS_PRODUCER
-                    mbar_arrive(empty_u32 + buf * 8);  // all 32 lanes: each orders its own fragment loads before the refill
-#else
                     __syncwarp();
                     if (lane == 0 && i + NBUF < nmine) {
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // helper's in-place stores before the refill
                         issue(i + NBUF, buf);
                     }
-#endif
                     if (has_next) {
                         while (seen_flag != want_flag) seen_flag = lds32_sync(rdy_u32 + nbuf * 8);
                     } else {
@@ -457,13 +393,13 @@ __global__ void __launch_bounds__(HessCfg<NB16, NHELP, ROWS>::LAUNCH_THREADS, 1)
                 const double y0 = transpose_reduce8(part0, g) + off0;
                 const double y1 = transpose_reduce8(part1, g) + off1;
                 if (valid) {
-                    const RowTerms2 rt = row_terms2(a.link, a.link1, y0, y1, ob);
+                    const RowTerms2 rt = row_terms2(a.link, a.link1, y0, y1, ob, a.fast != 0);
                     bad_domain |= !rt.ok;
                     const double wt = a.weights ? a.weights[row] : 1.0;
                     objacc += wt * rt.l;
                     rr = wt * rt.r0;
                     ww = wt * rt.w00;
-                    sc = sqrt(fabs(ww));
+                    sc = (rt.sw00 >= 0.0) ? (a.weights ? sqrt(wt) * rt.sw00 : rt.sw00) : sqrt(fabs(ww));
                     a.out_r1[row] = wt * rt.r1;
                     a.out_w01[row] = wt * rt.w01;
                     a.out_w11[row] = wt * rt.w11;

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) rowterms_kernel(const RowTermsArgs a) {
             a.w00[i] = wt * t.w;
             bad |= !t.ok;
         } else {
-            const RowTerms2 t = row_terms2(a.link0, a.link1, a.y0[i], a.y1[i], a.obs[i]);
+            const RowTerms2 t = row_terms2(a.link0, a.link1, a.y0[i], a.y1[i], a.obs[i], a.fast != 0);
             const double wt = a.weights ? a.weights[i] : 1.0;
             l += wt * t.l;
             a.r0[i] = wt * t.r0; a.r1[i] = wt * t.r1;

@@ -169,11 +169,32 @@ struct LogProduct {
 //   l = 1/2 log v + 1/2 (obs-mu)^2 / v
 struct RowTerms2 {
     double l, r0, r1, w00, w01, w11;
+    double sw00;  // sqrt(|w00|) when it comes for free (fast path), else < 0
     bool ok;
 };
 
-__device__ __forceinline__ RowTerms2 row_terms2(int link0, int link1, double y0, double y1, double obs) {
+__device__ __forceinline__ RowTerms2 row_terms2(int link0, int link1, double y0, double y1, double obs, bool fast = false) {
     RowTerms2 o;
+    o.sw00 = -1.0;
+    if (fast && link0 == LINK_IDENTITY && link1 == LINK_EXP) {
+        // mean = y0, variance = e^{y1}: one exp per row and no log, division or square root.
+        // h = e^{-y1/2} = 1/sqrt(v); with a = res/v and b = res^2/v the general expressions below reduce to
+        //   l = (y1 + b)/2, r0 = -a, r1 = (1 - b)/2, w00 = 1/v, w01 = a, w11 = b/2
+        const double h = exp(-0.5 * y1);
+        const double iv = h * h;
+        const double res = obs - y0;
+        const double a = res * iv;
+        const double b = res * a;
+        o.ok = true;
+        o.l = 0.5 * (y1 + b);
+        o.r0 = -a;
+        o.r1 = 0.5 - 0.5 * b;
+        o.w00 = iv;
+        o.w01 = a;
+        o.w11 = 0.5 * b;
+        o.sw00 = h;
+        return o;
+    }
     const LinkVal f0 = link_eval(link0, y0);
     const LinkVal f1 = link_eval(link1, y1);
     o.ok = f0.ok && f1.ok;

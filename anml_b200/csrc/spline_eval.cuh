@@ -65,8 +65,17 @@ struct BandedCfg {
 
 // EXTRAS: any of obs_se / offset / weights is present (compile-time, so that the plain case -- x and obs
 // only, BASELINE config #3 -- keeps two loads per row pair and a small register footprint)
+// Row pairs fetched ahead of the one being processed, per thread (registers), and resident CTAs per SM.
+// The loop is bound by HBM latency: ~35 KB must be in flight per SM to saturate the memory system
+// (2 CTAs x 256 threads x 3 pairs x 32 B = 48 KB in the plain case).
+#ifndef ANML_BANDED_DEPTH
+#define ANML_BANDED_DEPTH 3
+#endif
+#ifndef ANML_BANDED_MINB
+#define ANML_BANDED_MINB 2
+#endif
 template <int DEG, bool HESS, bool EXTRAS>
-__global__ void __launch_bounds__(256, EXTRAS ? 2 : 3) spline_banded_eval_kernel(const BandedArgs a) {
+__global__ void __launch_bounds__(256, EXTRAS ? 2 : ANML_BANDED_MINB) spline_banded_eval_kernel(const BandedArgs a) {
     using C = BandedCfg<DEG>;
     constexpr int NG = C::NG, NH = C::NH, NM = C::NM;
     __shared__ double red[8][NM + 1];
@@ -161,14 +170,19 @@ __global__ void __launch_bounds__(256, EXTRAS ? 2 : 3) spline_banded_eval_kernel
         };
         // pairs (2p, 2p+1) that overlap [ra, rb); only the first and last pair can be partial
         const long long p0 = ra >> 1, p1 = (rb + 1) >> 1;
+        constexpr int DEPTH = EXTRAS ? 2 : ANML_BANDED_DEPTH;
         long long p = p0 + threadIdx.x;
-        Pair cur = load(p, p < p1);
+        Pair ahead[DEPTH];
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) ahead[d] = load(p + d * C::THREADS, p + d * C::THREADS < p1);
         for (; p < p1; p += C::THREADS) {
-            const Pair nxt = load(p + C::THREADS, p + C::THREADS < p1);
+            const Pair cur = ahead[0];
+#pragma unroll
+            for (int d = 0; d + 1 < DEPTH; ++d) ahead[d] = ahead[d + 1];
+            ahead[DEPTH - 1] = load(p + DEPTH * C::THREADS, p + DEPTH * C::THREADS < p1);
             const long long i0 = 2 * p;
             if (i0 >= ra) row(cur.x.x, cur.ob.x, cur.se.x, cur.off.x, cur.wt.x);
             if (i0 + 1 < rb) row(cur.x.y, cur.ob.y, cur.se.y, cur.off.y, cur.wt.y);
-            cur = nxt;
         }
         // ---- CTA reduction of the run's moments (fixed order) -> record
 #pragma unroll

@@ -153,7 +153,7 @@ def test_wide_designs_use_the_blocked_hessian_kernel(n, p):
     check(gpu_eval("binomial", X, obs, se, off, link, x), want)
 
 
-def gpu_eval_meanvar(X0, X1, obs, x, links=("identity", "exp"), share=False):
+def gpu_eval_meanvar(X0, X1, obs, x, links=("identity", "exp"), share=False, options=(), want_hess=True):
     from anml_b200 import _native as N
 
     n = X0.shape[0]
@@ -166,6 +166,10 @@ def gpu_eval_meanvar(X0, X1, obs, x, links=("identity", "exp"), share=False):
     model.set_param(0, d0, N.LINK_CODES[LINK_NAME[links[0]]])
     model.set_param(1, d1, N.LINK_CODES[LINK_NAME[links[1]]])
     model.set_obs(obs)
+    for name, val in options:
+        model.set_option(name, val)
+    if not want_hess:
+        return model.eval(x, N.WANT_OBJ | N.WANT_GRAD)
     return model.eval(x)
 
 
@@ -182,6 +186,12 @@ def test_two_parameter_mean_variance_model(p0, p1, share):
     x = np.concatenate([0.7 * b0, 0.7 * b1])
     want = O.model_eval_fused("gaussian_meanvar", obs, [X0, X1], ["identity", "exp"], x)
     check(gpu_eval_meanvar(X0, X1, obs, x, share=share), want)
+    # the general row-term expressions (no identity/exp shortcut) and the gradient-only evaluation
+    check(gpu_eval_meanvar(X0, X1, obs, x, share=share, options=(("no_fast_math_paths", 1),)), want)
+    o, g, _ = gpu_eval_meanvar(X0, X1, obs, x, share=share, want_hess=False)
+    assert abs(o - want[0]) <= 1e-10 * abs(want[0]) and np.abs(g - want[1]).max() <= 1e-10 * np.abs(want[1]).max()
+    if share and p0 <= 64:  # without the warp-specialised kernel: dual-predictor pass + term-fed blocks
+        check(gpu_eval_meanvar(X0, X1, obs, x, share=share, options=(("no_warp_specialisation", 1),)), want)
 
 
 @pytest.mark.parametrize("share,p", [(True, 9), (False, 9), (True, 70)])

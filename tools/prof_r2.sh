@@ -20,4 +20,11 @@ run_plain $B --config c4 --rows 1e7 && {
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_bench_c4_rows1e7.csv $B --config c4 --rows 1e7 > gpurun_out/ncu5.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:fused_hess -s 6 -c 3 -o gpurun_out/r2_fused_hess_c4 $B --config c4 --rows 1e7 > gpurun_out/ncu6.log 2>&1
 }
-ls -la gpurun_out/*.ncu-rep
+# gpurun brings back at most 64 MiB: keep the metric extracts (and the raw pages), drop the reports
+for r in gpurun_out/r2_*.ncu-rep; do
+  python tools/summarize_ncu.py $r > ${r%.ncu-rep}_ncu.csv
+  ncu -i $r --page source --csv > ${r%.ncu-rep}_source.csv 2>/dev/null
+  gzip -f ${r%.ncu-rep}_source.csv
+  rm -f $r
+done
+ls -la gpurun_out/ | tail -20
