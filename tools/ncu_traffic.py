@@ -30,7 +30,7 @@ def main():
         for r in csv.DictReader(open(path)):
             # ncu prints template booleans as 0/1 or false/true depending on the version
             name = squash(r["kernel"]).replace("false", "0").replace("true", "1")
-            if squash(sig) not in name and squash(sig).split("<")[0] not in name:
+            if squash(sig) not in name:
                 continue
             if r["metric"] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and r["metric"] not in seen:
                 total += float(r["value"]) * UNIT[r["unit"]]
