@@ -1289,14 +1289,16 @@ static int run_fused_block(anml_model* m, const anml_design* d, FusedArgs a, boo
         break;
     if (specialised) {
         const bool sgn = !weights_positive(a.family, a.link, a.fast != 0) || m->force_signed;
-// helper warps per team: 2 at full width (registers: setmaxnreg 216 / 144); narrow designs are paced by
-// the helpers' per-row work, not by the tensor warp, and their accumulators are few: more helpers there
+// helper warps per team: 2 at full width (registers: setmaxnreg 216 / 144).  Designs of at most 16 columns
+// are paced by the helpers' per-row work (3 accumulator tiles keep the tensor warp idle most of the time):
+// p = 16, n = 5e7: 2 helpers 1.70 ms, 3 helpers 1.41, 4 helpers 1.27 (profiles/r2_ab_narrow.txt).  At 17-32
+// columns more helpers lose (p = 22: 2.92 -> 2.97 -> 3.65 ms): the tensor warp sets the pace there.
 #ifndef ANML_NARROW_NHELP
-#define ANML_NARROW_NHELP 2
+#define ANML_NARROW_NHELP 4
 #endif
 #define HESS_CASE(NB)                                                                              \
     case NB: {                                                                                     \
-        constexpr int NH = (NB <= 2) ? ANML_NARROW_NHELP : 2;                                      \
+        constexpr int NH = (NB == 1) ? ANML_NARROW_NHELP : 2;                                      \
         if (mode == 3) rc = launch_hess_t<NB, NH, true, 3>(d, a, grid, st);                        \
         else if (mode == 1) rc = launch_hess_t<NB, NH, true, 1>(d, a, grid, st);                   \
         else rc = sgn ? launch_hess_t<NB, NH, true, 0>(d, a, grid, st) : launch_hess_t<NB, NH, false, 0>(d, a, grid, st); \

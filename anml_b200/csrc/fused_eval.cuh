@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(256, 1) fused_eval_kernel(const __grid_constan
             continue;
         } else {
             if (valid) {
-                rr = a.rvec[row];
+                if (a.rvec) rr = a.rvec[row];  // (null: cross block of two parameters, Hessian only)
                 ww = HESS ? a.wvec[row] : 0.0;
             }
         }

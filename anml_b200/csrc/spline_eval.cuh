@@ -66,13 +66,13 @@ struct BandedCfg {
 // EXTRAS: any of obs_se / offset / weights is present (compile-time, so that the plain case -- x and obs
 // only, BASELINE config #3 -- keeps two loads per row pair and a small register footprint)
 // Row pairs fetched ahead of the one being processed, per thread (registers), and resident CTAs per SM.
-// The loop is bound by HBM latency: ~35 KB must be in flight per SM to saturate the memory system
-// (2 CTAs x 256 threads x 3 pairs x 32 B = 48 KB in the plain case).
+// Measured at n = 5e7 (profiles/r2_ab_banded.txt): 3 CTAs x 1 pair ahead 0.180 ms; 2 CTAs x 2 / 3 / 4 pairs ahead
+// 0.223 / 0.223 / 0.225 ms; 3 CTAs x 2 pairs ahead spills (0.306 ms).  Occupancy beats prefetch depth here.
 #ifndef ANML_BANDED_DEPTH
-#define ANML_BANDED_DEPTH 3
+#define ANML_BANDED_DEPTH 1
 #endif
 #ifndef ANML_BANDED_MINB
-#define ANML_BANDED_MINB 2
+#define ANML_BANDED_MINB 3
 #endif
 template <int DEG, bool HESS, bool EXTRAS>
 __global__ void __launch_bounds__(256, EXTRAS ? 2 : ANML_BANDED_MINB) spline_banded_eval_kernel(const BandedArgs a) {
