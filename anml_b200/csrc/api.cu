@@ -1789,9 +1789,9 @@ extern "C" int anml_model_main_kernel(const anml_model* m, char* out, int out_le
 struct anml_comm {
     int device = 0, rank = 0, world = 1, sm_count = 0;
     long long max_elems = 0;
-    unsigned long long epoch = 0;
-    unsigned long long* window = nullptr;               // local, cudaMalloc'ed, exported
-    unsigned long long* peer[COMM_MAX_WORLD] = {};       // mapped windows, peer[rank] == window
+    unsigned int epoch = 0;
+    unsigned char* window = nullptr;                    // local, cudaMalloc'ed, exported
+    unsigned char* peer[COMM_MAX_WORLD] = {};           // mapped windows, peer[rank] == window
     bool connected = false;
     long long timeout_cycles = 0;
 };
@@ -1805,6 +1805,7 @@ extern "C" int anml_comm_handle_bytes(int* out) {
 extern "C" int anml_comm_create(int device, int rank, int world, int64_t max_elems, anml_comm** out) {
     if (!out || world < 1 || world > COMM_MAX_WORLD || rank < 0 || rank >= world || max_elems <= 0)
         return fail(ANML_EINVAL, "anml_comm_create: need 0 <= rank < world <= %d and max_elems > 0", COMM_MAX_WORLD);
+    if (max_elems > (1LL << 22)) return fail(ANML_EUNSUPPORTED, "anml_comm_create: the peer window is meant for latency-bound records (at most 2^22 doubles); use NCCL for larger ones");
     CU_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, device));
@@ -1816,7 +1817,8 @@ extern "C" int anml_comm_create(int device, int rank, int world, int64_t max_ele
         const double v = atof(s);
         if (v > 0.0) c->timeout_cycles = (long long)(v * 1e3 * (double)prop.clockRate);
     }
-    const size_t bytes = (size_t)COMM_HEADER_U64 * 8 + (size_t)2 * max_elems * sizeof(double);
+    // header | slot[2 parities][world sources][max_elems] of 16-byte entries
+    const size_t bytes = (size_t)COMM_HEADER_BYTES + (size_t)2 * world * max_elems * 16;
     cudaError_t e = cudaMalloc(&c->window, bytes);
     if (e == cudaSuccess) e = cudaMemset(c->window, 0, bytes);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -1860,7 +1862,7 @@ extern "C" int anml_comm_connect(anml_comm* c, const void* all_handles) {
                 }
             return fail(ANML_ECUDA, "cudaIpcOpenMemHandle for rank %d failed: %s", j, cudaGetErrorString(e));
         }
-        c->peer[j] = static_cast<unsigned long long*>(ptr);
+        c->peer[j] = static_cast<unsigned char*>(ptr);
     }
     c->connected = true;
     return ANML_OK;
@@ -1874,10 +1876,11 @@ extern "C" int anml_comm_allreduce_async(anml_comm* c, double* buf_dev, int64_t 
     CommArgs a;
     memset(&a, 0, sizeof(a));
     a.buf = buf_dev; a.n = n_elems; a.max_elems = c->max_elems; a.rank = c->rank; a.world = c->world;
-    a.epoch = ++c->epoch; a.local = c->window; a.timeout_cycles = c->timeout_cycles;
+    if (++c->epoch == 0) c->epoch = 2;  // never 0 (the window's initial state); keep the parity sequence alternating
+    a.epoch = c->epoch; a.local = c->window; a.timeout_cycles = c->timeout_cycles;
     for (int j = 0; j < c->world; ++j) a.peer[j] = c->peer[j];
-    long long grid = (n_elems + 511) / 512;  // two elements per thread, at most one CTA per SM (all co-resident while waiting)
-    if (grid > c->sm_count) grid = c->sm_count;
+    long long grid = (n_elems + 255) / 256;  // one element per thread up to two waves, then a grid-stride loop
+    if (grid > 2LL * c->sm_count) grid = 2LL * c->sm_count;
     if (grid < 1) grid = 1;
     comm_allreduce_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(a);
     CU_TRY(cudaGetLastError());
@@ -1888,7 +1891,7 @@ extern "C" int anml_comm_error(anml_comm* c, int64_t* failed_epoch) {
     if (!c || !failed_epoch) return fail(ANML_EINVAL, "NULL argument");
     CU_TRY(cudaSetDevice(c->device));
     unsigned long long v = 0;
-    CU_TRY(cudaMemcpy(&v, c->window + COMM_MAX_WORLD + 1, sizeof(v), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(&v, c->window, sizeof(v), cudaMemcpyDeviceToHost));
     *failed_epoch = (int64_t)v;
     return ANML_OK;
 }

@@ -10,11 +10,13 @@ is counted once.
 One process per GPU (``torchrun``); ``torch.distributed`` is the plumbing
 (rendezvous, the handle exchange, barriers).  On the evaluation path itself:
 
-* the sum runs over **peer memory**: one kernel per evaluation reads every
-  rank's record through NVLink in rank order (``csrc/comm.cuh``,
-  :class:`PeerAllReduce`) -- about half the latency of the NCCL all-reduce it
-  replaces, and every rank gets the same bits.  ``ANML_B200_COLLECTIVE=nccl``
-  (or a failed peer mapping) selects ``dist.all_reduce`` instead;
+* the sum runs over **peer memory**: one kernel per evaluation pushes the
+  rank's record, value and flag in the same 16-byte store, into every peer's
+  window over NVLink and sums what arrives in its own window in rank order
+  (``csrc/comm.cuh``, :class:`PeerAllReduce`): no fence, no second round trip,
+  and every rank gets the same bits.  Records above 512 KB (P > 250),
+  ``ANML_B200_COLLECTIVE=nccl`` or a failed peer mapping select
+  ``dist.all_reduce`` instead;
 * rank 0 hands the coefficient vector to the serving ranks through a host
   shared-memory mailbox (:class:`ShmMailbox`; one node, so ``/dev/shm`` reaches
   everybody) instead of an NCCL broadcast plus a device-to-host copy per rank.
@@ -33,6 +35,7 @@ from typing import Optional, Tuple
 import numpy as np
 
 OP_STOP, OP_EVAL_HESS, OP_EVAL_GRAD = 0.0, 1.0, 2.0
+PEER_MAX_ELEMS = 1 << 16  # packed records up to 512 KB go through the peer-memory kernel, larger ones through NCCL
 
 
 def shard_rows(n: int, world: int, rank: int) -> Tuple[int, int]:
@@ -215,17 +218,19 @@ class ShardedModel:
             self._setup_fast_paths()
 
     def _check_prior_placement(self):
-        """The Gaussian prior must be enabled on exactly one rank, or it is counted ``world`` times --
-        silently: the fit still converges.  Checked once, collectively."""
+        """A Gaussian prior must be enabled on exactly one rank, or it is counted ``world`` times --
+        silently: the fit still converges.  Checked once, collectively (models without a prior pass)."""
         model = getattr(self.local, "model", None)
         if model is None or not hasattr(model, "prior_enabled"):
             return
         torch, dist = self.torch, self.dist
         dev = self.local.packed.device if self._on_gpu else torch.device("cpu")
-        flag = torch.tensor([1 if model.prior_enabled else 0], dtype=torch.int32, device=dev)
+        has = bool(getattr(model, "has_gaussian_prior", True))
+        flag = torch.tensor([1 if has else 0, 1 if (has and model.prior_enabled) else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(flag, group=self.group)
-        if int(flag.item()) != 1:
-            raise ValueError(f"the prior is enabled on {int(flag.item())} ranks; call model.set_prior_enabled(rank == 0) "
+        carriers, enabled = int(flag[0].item()), int(flag[1].item())
+        if carriers > 0 and enabled != 1:
+            raise ValueError(f"the prior is enabled on {enabled} ranks; call model.set_prior_enabled(rank == 0) "
                              "so that it is counted exactly once")
 
     def _setup_fast_paths(self):
@@ -234,7 +239,10 @@ class ShardedModel:
         import os
 
         torch, dist = self.torch, self.dist
-        if self._on_gpu and os.environ.get("ANML_B200_COLLECTIVE", "peer").lower() != "nccl":
+        # the peer window serves latency-bound records; from ~0.5 MB up (P > 250) NCCL's bandwidth-optimal
+        # algorithms win (measured at 8.4 MB on 2 GPUs: NCCL 44 us, one-shot peer reads 81 us)
+        small = self.local.packed.numel() <= PEER_MAX_ELEMS if self._on_gpu else False
+        if self._on_gpu and small and os.environ.get("ANML_B200_COLLECTIVE", "peer").lower() != "nccl":
             try:
                 self._peer = PeerAllReduce(self.local.packed.device.index, self.local.packed.numel(), self.group)
             except Exception as exc:  # every rank raises together (the constructor agrees on the outcome)

@@ -54,6 +54,7 @@ class Model:
         self._cache_key = None
         self._cache = None
         self.prior_enabled = True
+        self.has_gaussian_prior = False  # set by attach: some parameter carries a finite Gaussian prior
         self.num_evaluations = 0
 
     # ---- sizes ---------------------------------------------------------------
@@ -149,12 +150,14 @@ class Model:
                 nm.set_obs_se(se)
         if weights is not None:
             nm.set_weights(weights)
+        self.has_gaussian_prior = False
         for k, p in enumerate(self.parameters):
             direct = p.prior_dict["direct"]["GaussianPrior"]
             linear = p.prior_dict["linear"]["GaussianPrior"]
             has_direct = bool(np.any(np.isfinite(direct.sd)))
             has_linear = linear.mat is not None and linear.mat.shape[0] > 0
             if has_direct or has_linear:
+                self.has_gaussian_prior = True
                 nm.set_gaussian_prior(k, direct.mean, direct.sd,
                                       linear.mat if has_linear else None,
                                       linear.mean if has_linear else None,

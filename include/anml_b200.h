@@ -181,10 +181,12 @@ int anml_model_set_option(anml_model* m, const char* name, int64_t value);
  * MPI, a file) and hands them to anml_comm_connect, then synchronises the ranks once.  After that
  *   anml_comm_allreduce_async(c, buf, n, stream)
  * sums buf (device, n <= max_elems doubles) over the ranks in place with ONE kernel launch on `stream`
- * (a cudaStream_t; NULL or cudaStreamLegacy = the legacy default stream): peers' records are read
- * through NVLink in rank order, so every rank gets the same bits.  Every rank must call it the same
- * number of times.  anml_comm_error reports the evaluation number at which a peer failed to arrive
- * within the timeout (ANML_B200_COMM_TIMEOUT_S, default 20 s; the record is then NaN), 0 if none. */
+ * (a cudaStream_t; NULL or cudaStreamLegacy = the legacy default stream): every element is pushed, value
+ * and evaluation number in the same 16-byte store, into every peer's window through NVLink and summed in
+ * rank order from the local window, so every rank gets the same bits.  Every rank must call it the same
+ * number of times.  Meant for latency-bound records (max_elems <= 2^22; the Python layer uses NCCL above
+ * 2^16 elements).  anml_comm_error reports the evaluation number at which a peer failed to arrive within
+ * the timeout (ANML_B200_COMM_TIMEOUT_S, default 20 s; the element is then NaN), 0 if none. */
 typedef struct anml_comm anml_comm;
 int anml_comm_handle_bytes(int* out);
 int anml_comm_create(int device, int rank, int world, int64_t max_elems, anml_comm** out);

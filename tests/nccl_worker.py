@@ -102,6 +102,7 @@ def main():
             assert np.array_equal(svar.spline.knots, want_knots)
             smodel = Model("gaussian", DataExample("obs", "obs_se"), [spar], device=local_rank)
             smodel.attach(sdf)
+            smodel.set_prior_enabled(rank == 0)
             assert smodel.banded_spline is True
             assert not spar.device_design.materialized  # the dense design of a banded model is never built
             ssh = ShardedModel(NativeLocalEvaluator(smodel, torch.device("cuda", local_rank)))
