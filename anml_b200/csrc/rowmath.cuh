@@ -61,69 +61,6 @@ __device__ __forceinline__ double link_order(int link, double y, int order, bool
     return order == 0 ? v.f : (order == 1 ? v.d1 : v.d2);
 }
 
-// ---- short exp / reciprocal for the fast paths -------------------------------------------------
-// In the warp-specialised Hessian kernel every FP64 instruction of a helper warp waits ~50 cycles for a
-// slot of the pipe the DMMA stream saturates, and the tensor warp waits for the helpers: the helpers' time
-// is their FP64 instruction count.  libdevice's exp is ~19 FP64 instructions (no table, degree-10
-// polynomial), the IEEE division ~9.  exp_short: e^x = 2^k * 2^(j/64) * e^r with a 64-entry table and a
-// degree-5 polynomial on |r| <= ln2/128 -- 10 FP64 instructions, <= 1 ulp (checked against a 60-digit
-// reference over [-700, 700]); the scale by 2^k is integer work on the exponent field.  Arguments that
-// could leave the normal range (|x| >= 708, inf, nan) take libdevice's exp.  rcp_short: MUFU.RCP64H seed +
-// two Newton steps (4 FMAs), <= 1 ulp, for arguments in the normal range (here s = 1 + z >= 1).
-__device__ const double EXP2_64TH[64] = {
-    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
-    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
-    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
-    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
-    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
-    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
-    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
-    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
-    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
-    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
-    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
-    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
-    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
-    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
-    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
-    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
-
-__device__ __forceinline__ double exp_short(double x) {
-#ifdef ANML_LIBDEVICE_EXP
-    return exp(x);
-#else
-    if ((unsigned)(__double2hiint(x) & 0x7fffffff) >= 0x40862000u) return exp(x);  // |x| >= 708, inf, nan
-    const double MAGIC = 0x1.8p52;                                                 // rounds to an integer in the low word
-    double kf = fma(x, 0x1.71547652b82fep+6 /* 64/ln2 */, MAGIC);
-    const int ki = __double2loint(kf);
-    kf -= MAGIC;
-    double r = fma(kf, -0x1.62e42fef80000p-7 /* ln2/64, 34 bits */, x);
-    r = fma(kf, -0x1.1cf79abc9e3b4p-42, r);
-    const double t = EXP2_64TH[ki & 63];
-    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-    p = fma(p, r, 1.0 / 6.0);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p *= r;
-    const double v = fma(t, p, t);
-    return __hiloint2double(__double2hiint(v) + ((ki >> 6) << 20), __double2loint(v));
-#endif
-}
-
-__device__ __forceinline__ double rcp_short(double s) {
-#ifdef ANML_LIBDEVICE_EXP
-    return 1.0 / s;
-#else
-    if ((unsigned)(__double2hiint(s) & 0x7fffffff) >= 0x7fd00000u) return 1.0 / s;  // huge, inf, nan: the IEEE path
-    double x;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(s));
-    double e = fma(-s, x, 1.0);
-    x = fma(x, e, x);
-    e = fma(-s, x, 1.0);
-    return fma(x, e, x);
-#endif
-}
-
 // Per-row terms of a one-parameter family, already chained through the link:
 //   l = NLL term, r = dl/dtheta * f', w = d2l/dtheta2 * f'^2 + dl/dtheta * f''
 // so that grad = X^T r and Hessian = X^T diag(w) X  (SURVEY.md 3.3).
@@ -147,10 +84,10 @@ __device__ __forceinline__ RowTerms1 row_terms1(int family, int link, bool fast,
     if (fast && family == FAM_BINOMIAL && link == LINK_EXPIT) {
         // canonical logistic: one exp, one log, one reciprocal per row.
         // h = exp(-y/2): z = h^2 and sqrt(w) = h q come for free (no sqrt).
-        const double h = exp_short(-0.5 * y);
+        const double h = exp(-0.5 * y);
         const double z = h * h;
         const double s = 1.0 + z;
-        const double q = rcp_short(s);
+        const double q = 1.0 / s;
         if (DEFER_LOG) {
             o.ls = s;
             o.l = (1.0 - obs) * y;
@@ -173,7 +110,7 @@ __device__ __forceinline__ RowTerms1 row_terms1(int family, int link, bool fast,
         return o;
     }
     if (fast && family == FAM_POISSON && link == LINK_EXP) {
-        const double h = exp_short(0.5 * y);
+        const double h = exp(0.5 * y);
         const double lam = h * h;
         o.l = lam - obs * y;
         o.r = lam - obs;
@@ -243,7 +180,7 @@ __device__ __forceinline__ RowTerms2 row_terms2(int link0, int link1, double y0,
         // mean = y0, variance = e^{y1}: one exp per row and no log, division or square root.
         // h = e^{-y1/2} = 1/sqrt(v); with a = res/v and b = res^2/v the general expressions below reduce to
         //   l = (y1 + b)/2, r0 = -a, r1 = (1 - b)/2, w00 = 1/v, w01 = a, w11 = b/2
-        const double h = exp_short(-0.5 * y1);
+        const double h = exp(-0.5 * y1);
         const double iv = h * h;
         const double res = obs - y0;
         const double a = res * iv;
