@@ -125,7 +125,7 @@ struct anml_model {
     double* se_owned = nullptr;
     double* weights_owned = nullptr;
     bool prior_enabled = true;
-    bool force_generic = false, no_fast = false, no_specialise = false;
+    bool force_generic = false, no_fast = false, no_specialise = false, banded_registers = false;
     bool force_signed = false;
     cudaStream_t stream = nullptr;
     int sm_count = 0;
@@ -1037,6 +1037,7 @@ extern "C" int anml_model_set_option(anml_model* m, const char* name, int64_t va
     else if (!strcmp(name, "no_fast_math_paths")) m->no_fast = value != 0;
     else if (!strcmp(name, "no_warp_specialisation")) m->no_specialise = value != 0;
     else if (!strcmp(name, "force_signed_weights")) m->force_signed = value != 0;
+    else if (!strcmp(name, "banded_register_prefetch")) m->banded_registers = value != 0;
     else return fail(ANML_EINVAL, "unknown option '%s'", name);
     return ANML_OK;
 }
@@ -1451,13 +1452,32 @@ static int eval_banded(anml_model* m, int want, double* packed, cudaStream_t st)
     EventPair* ep = next_events(m);
     if (ep) CU_TRY(cudaEventRecord(ep->a, st));
     const bool extras = a.se || a.offset || a.weights;
-#define BANDED_LAUNCH(D)                                                                      \
-    if (extras) {                                                                             \
-        if (hess) spline_banded_eval_kernel<D, true, true><<<b.grid, 256, 0, st>>>(a);        \
-        else spline_banded_eval_kernel<D, false, true><<<b.grid, 256, 0, st>>>(a);            \
-    } else {                                                                                  \
-        if (hess) spline_banded_eval_kernel<D, true, false><<<b.grid, 256, 0, st>>>(a);       \
-        else spline_banded_eval_kernel<D, false, false><<<b.grid, 256, 0, st>>>(a);           \
+    const int nv = 2 + (a.se ? 1 : 0) + (a.offset ? 1 : 0) + (a.weights ? 1 : 0);
+    const size_t bulk_smem = (size_t)BULK_STAGES * nv * BULK_ROWS * sizeof(double);
+    const bool bulk = !m->banded_registers;
+    // the bulk-copy kernel (row vectors staged through shared memory by cp.async.bulk) is the default; the
+    // register-prefetch kernel stays selectable ("banded_register_prefetch") for A/B runs
+#define BANDED_ONE(KERN, D, H, E)                                                                                   \
+    {                                                                                                               \
+        if (bulk) {                                                                                                 \
+            static ConfiguredOn configured;                                                                         \
+            if ((E) && !configured.has(m->device)) {                                                                \
+                CU_TRY(cudaFuncSetAttribute(spline_banded_bulk_kernel<D, H, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                            (int)(BULK_STAGES * 5 * BULK_ROWS * sizeof(double))));                  \
+                configured.set(m->device);                                                                          \
+            }                                                                                                       \
+            spline_banded_bulk_kernel<D, H, E><<<b.grid, 256, bulk_smem, st>>>(a);                                  \
+        } else {                                                                                                    \
+            spline_banded_eval_kernel<D, H, E><<<b.grid, 256, 0, st>>>(a);                                          \
+        }                                                                                                           \
+    }
+#define BANDED_LAUNCH(D)                                  \
+    if (extras) {                                         \
+        if (hess) BANDED_ONE(_, D, true, true)            \
+        else BANDED_ONE(_, D, false, true)                \
+    } else {                                              \
+        if (hess) BANDED_ONE(_, D, true, false)           \
+        else BANDED_ONE(_, D, false, false)               \
     }
     switch (b.degree) {
         case 1: BANDED_LAUNCH(1) break;
@@ -1465,9 +1485,11 @@ static int eval_banded(anml_model* m, int want, double* packed, cudaStream_t st)
         default: BANDED_LAUNCH(3) break;
     }
 #undef BANDED_LAUNCH
+#undef BANDED_ONE
     CU_TRY(cudaGetLastError());
     if (ep) CU_TRY(cudaEventRecord(ep->b, st));
-    snprintf(g_kernel, sizeof(g_kernel), "spline_banded_eval_kernel<%d, %d, %d>", b.degree, hess ? 1 : 0, extras ? 1 : 0);
+    snprintf(g_kernel, sizeof(g_kernel), "%s<%d, %d, %d>", bulk ? "spline_banded_bulk_kernel" : "spline_banded_eval_kernel", b.degree, hess ? 1 : 0,
+             extras ? 1 : 0);
     m->main_kernel = g_kernel;
     banded_reduce_kernel<<<(b.rec + 31) / 32, dim3(32, 32), 0, st>>>(b.partials, b.grid, b.rec, b.reduced);
     CU_TRY(cudaGetLastError());

@@ -85,6 +85,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tma
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
         : "memory");
 }
+// 1-D bulk copy global -> shared (16-byte aligned, size a multiple of 16), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }

@@ -219,6 +219,181 @@ __global__ void __launch_bounds__(256, EXTRAS ? 2 : ANML_BANDED_MINB) spline_ban
     if (bad_domain) atomicOr(a.status, 1);
 }
 
+// ---- the same evaluation with the row vectors staged through shared memory by bulk async copies ----
+// The register-prefetch kernel above keeps 24 warps x 1 row pair in flight per SM (~25 KB): not enough
+// outstanding bytes to saturate HBM (ncu: DRAM 56 % busy, long-scoreboard stalls 5.2 per issue), and a
+// deeper register prefetch costs the occupancy it needs (profiles/r2_ab_banded.txt).  Here thread 0 of
+// the CTA streams the CTA's slice in chunks of BULK_ROWS rows per vector with cp.async.bulk (the TMA
+// engine, completion on an mbarrier) into a ring of BULK_STAGES stages: (stages - 1) x vectors x 4 KB in
+// flight per CTA whatever the register budget, and every thread reads its two rows of a chunk with one
+// 16-byte shared-memory load per vector.  Runs of constant knot interval are walked inside the chunk
+// loop: a chunk that holds a run boundary is simply visited by both runs.
+constexpr int BULK_ROWS = 512;   // per chunk and vector: 4 KB
+constexpr int BULK_STAGES = 4;
+
+template <int DEG, bool HESS, bool EXTRAS>
+__global__ void __launch_bounds__(256, EXTRAS ? 2 : 3) spline_banded_bulk_kernel(const BandedArgs a) {
+    using C = BandedCfg<DEG>;
+    constexpr int NG = C::NG, NH = C::NH, NM = C::NM;
+    extern __shared__ __align__(128) unsigned char bulk_smem[];
+    __shared__ double red[8][NM + 1];
+    __shared__ __align__(8) unsigned long long full_bar[BULK_STAGES];
+    const int nint = a.nk - 1;
+    const int rec = nint * NM + 1;
+    double* out = a.partials + (size_t)blockIdx.x * rec;
+    for (int i = threadIdx.x; i < rec; i += blockDim.x) out[i] = 0.0;  // intervals this CTA never meets
+
+    const long long lo = (long long)blockIdx.x * a.rows_per_cta;  // even
+    long long hi = lo + a.rows_per_cta;
+    if (hi > a.n) hi = a.n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool has_se = EXTRAS && a.se != nullptr, has_off = EXTRAS && a.offset != nullptr, has_wt = EXTRAS && a.weights != nullptr;
+    // vectors of a stage: x, obs, then the extras that are present
+    const double* vec[5] = {a.xs, a.obs, nullptr, nullptr, nullptr};
+    int nv = 2, i_se = -1, i_off = -1, i_wt = -1;
+    if (has_se) { i_se = nv; vec[nv++] = a.se; }
+    if (has_off) { i_off = nv; vec[nv++] = a.offset; }
+    if (has_wt) { i_wt = nv; vec[nv++] = a.weights; }
+    const uint32_t stage_bytes = (uint32_t)nv * BULK_ROWS * 8;
+    const uint32_t ring = smem_u32(bulk_smem);
+    const uint32_t bars = smem_u32(full_bar);
+    const long long nchunks = lo < hi ? (hi - lo + BULK_ROWS - 1) / BULK_ROWS : 0;
+
+    auto issue = [&](long long c) {  // thread 0: chunk c -> stage c % BULK_STAGES
+        const int s = (int)(c % BULK_STAGES);
+        const long long cs = lo + c * BULK_ROWS;
+        long long rows = hi - cs < BULK_ROWS ? hi - cs : BULK_ROWS;
+        rows += rows & 1;  // 16-byte granules; the arrays carry two spare doubles
+        const uint32_t bytes = (uint32_t)rows * 8;
+        mbar_arrive_expect_tx(bars + s * 8, bytes * nv);
+#pragma unroll
+        for (int v = 0; v < 5; ++v)
+            if (v < nv) bulk_load_1d(ring + s * stage_bytes + v * BULK_ROWS * 8, vec[v] + cs, bytes, bars + s * 8);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < BULK_STAGES; ++s) mbar_init(bars + s * 8, 1);
+        mbar_fence_init();
+        for (long long c = 0; c < nchunks && c < BULK_STAGES; ++c) issue(c);
+    }
+    double objacc = 0.0;
+    bool bad_domain = false;
+    __syncthreads();  // barriers initialised; the zero fill above is ordered before the run results below
+
+    int k = 0;
+    if (lo < hi) {
+        while (k < nint - 1 && a.seg[k + 1] <= lo) ++k;
+    }
+    double knot = 0.0, d[DEG + 1], G[NG], M[NH];
+    auto begin_run = [&]() {
+        knot = a.knots[k];
+#pragma unroll
+        for (int j = 0; j <= DEG; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q <= DEG; ++q) s = fma(a.coef[(k * (DEG + 1) + q) * (DEG + 1) + j], a.beta[k + q], s);
+            d[j] = s;
+        }
+#pragma unroll
+        for (int j = 0; j < NG; ++j) G[j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NH; ++j) M[j] = 0.0;
+    };
+    auto end_run = [&]() {  // CTA reduction of the run's moments (fixed order) -> record
+#pragma unroll
+        for (int j = 0; j < NG; ++j) G[j] = warp_sum(G[j]);
+        if (HESS) {
+#pragma unroll
+            for (int j = 0; j < NH; ++j) M[j] = warp_sum(M[j]);
+        }
+        __syncthreads();  // red[] of the previous run has been read
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < NG; ++j) red[warp][j] = G[j];
+#pragma unroll
+            for (int j = 0; j < NH; ++j) red[warp][NG + j] = HESS ? M[j] : 0.0;
+        }
+        __syncthreads();
+        if (threadIdx.x < NM) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+            out[k * NM + threadIdx.x] = s;
+        }
+    };
+    auto row = [&](double x, double ob, double se, double off, double wt) {
+        const double u = x - knot;
+        double y = d[DEG];
+#pragma unroll
+        for (int j = DEG - 1; j >= 0; --j) y = fma(y, u, d[j]);
+        const RowTerms1 rt = row_terms1<false>(a.family, a.link, a.fast != 0, y + off, ob, se);
+        bad_domain |= !rt.ok;
+        double l = rt.l, r = rt.r, w = rt.w;
+        if (has_wt) {
+            l *= wt; r *= wt; w *= wt;
+        }
+        objacc += l;
+        double pw[NH];  // u^s
+        pw[0] = 1.0;
+        if (NH > 1) pw[1] = u;
+#pragma unroll
+        for (int s = 2; s < NH; ++s) pw[s] = pw[s >> 1] * pw[s - (s >> 1)];
+        G[0] += r;
+#pragma unroll
+        for (int j = 1; j < NG; ++j) G[j] = fma(r, pw[j], G[j]);
+        if (HESS) {
+            M[0] += w;
+#pragma unroll
+            for (int s = 1; s < NH; ++s) M[s] = fma(w, pw[s], M[s]);
+        }
+    };
+
+    if (lo < hi) begin_run();
+    for (long long c = 0; c < nchunks; ++c) {
+        const int s = (int)(c % BULK_STAGES);
+        mbar_wait(bars + s * 8, (uint32_t)((c / BULK_STAGES) & 1));
+        const long long cs = lo + c * BULK_ROWS;
+        const long long ce = cs + BULK_ROWS < hi ? cs + BULK_ROWS : hi;
+        // this thread's two rows of the chunk
+        const uint32_t at = ring + s * stage_bytes + threadIdx.x * 16;
+        const double2 x2 = lds128(at), ob2 = lds128(at + BULK_ROWS * 8);
+        double2 se2 = make_double2(1.0, 1.0), of2 = make_double2(0.0, 0.0), wt2 = make_double2(1.0, 1.0);
+        if (EXTRAS) {
+            if (has_se) se2 = lds128(at + i_se * BULK_ROWS * 8);
+            if (has_off) of2 = lds128(at + i_off * BULK_ROWS * 8);
+            if (has_wt) wt2 = lds128(at + i_wt * BULK_ROWS * 8);
+        }
+        const long long r0 = cs + 2 * threadIdx.x;
+        long long pos = cs;
+        while (pos < ce) {
+            long long run_end = a.seg[k + 1] < hi ? a.seg[k + 1] : hi;
+            const long long stop = ce < run_end ? ce : run_end;
+            if (r0 >= pos && r0 < stop) row(x2.x, ob2.x, se2.x, of2.x, wt2.x);
+            if (r0 + 1 >= pos && r0 + 1 < stop) row(x2.y, ob2.y, se2.y, of2.y, wt2.y);
+            pos = stop;
+            if (pos == run_end && pos < hi) {  // the run ends inside (or at the end of) this chunk
+                end_run();
+                ++k;
+                while (k < nint - 1 && a.seg[k + 1] <= pos) ++k;  // empty intervals (repeated knots)
+                begin_run();
+            }
+        }
+        __syncthreads();  // every thread has read the stage
+        if (threadIdx.x == 0 && c + BULK_STAGES < nchunks) issue(c + BULK_STAGES);
+    }
+    if (lo < hi) end_run();
+    objacc = warp_sum(objacc);
+    __syncthreads();
+    if (lane == 0) red[warp][NM] = objacc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][NM];
+        out[rec - 1] = s;
+    }
+    if (bad_domain) atomicOr(a.status, 1);
+}
+
 // Taylor coefficients of every basis piece about the left knot of its interval: one thread per
 // (interval, derivative order)
 template <int DEG>

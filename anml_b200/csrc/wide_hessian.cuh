@@ -41,11 +41,6 @@ struct WideArgs {
     double* partials;     // [nchunks][npairs][128*64]
 };
 
-__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
 // pair -> (bi: 128-column block of Xa, bj: 64-column block of Xb)
 __device__ __forceinline__ void pair_to_blocks(int pair, int symmetric, int nbj, int& bi, int& bj) {
     if (symmetric) {

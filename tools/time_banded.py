@@ -16,6 +16,9 @@ m = N.NativeModel(n, "gaussian", 1)
 m.set_param(0, d, N.LINK_CODES["Identity"])
 m.set_obs(dev_ptr=obs.data_ptr(), keepalive=obs)
 assert m.enable_banded_spline(knots, deg, x_dev_ptr=xs.data_ptr())
+for kv in sys.argv[2:]:  # e.g. banded_register_prefetch=1
+    k, v = kv.split("=")
+    m.set_option(k, int(v))
 x = np.linspace(-1, 1, nb)
 for _ in range(5): m.eval(x)
 m.kernel_time(reset=True)
@@ -26,4 +29,4 @@ kms, _, _ = m.kernel_time(reset=True)
 for _ in range(30): m.eval(x, N.WANT_OBJ | N.WANT_GRAD)
 kg, _, _ = m.kernel_time(reset=True)
 print(json.dumps({"n": n, "kernel_ms": kms / 30, "objgrad_kernel_ms": kg / 30, "eval_ms": e2e, "GBps": 16.0 * n / (kms / 30) / 1e6,
-                  "obj": o, "materialized": d.materialized}))
+                  "obj": o, "materialized": d.materialized, "kernel": m.main_kernel()}))
