@@ -1453,7 +1453,7 @@ static int eval_banded(anml_model* m, int want, double* packed, cudaStream_t st)
     if (ep) CU_TRY(cudaEventRecord(ep->a, st));
     const bool extras = a.se || a.offset || a.weights;
     const int nv = 2 + (a.se ? 1 : 0) + (a.offset ? 1 : 0) + (a.weights ? 1 : 0);
-    const size_t bulk_smem = (size_t)BULK_STAGES * nv * BULK_ROWS * sizeof(double);
+    const size_t bulk_smem = (size_t)BULK_STAGES * nv * (extras ? BULK_ROWS_EXTRAS : BULK_ROWS_PLAIN) * sizeof(double);
     const bool bulk = !m->banded_registers;
     // the bulk-copy kernel (row vectors staged through shared memory by cp.async.bulk) is the default; the
     // register-prefetch kernel stays selectable ("banded_register_prefetch") for A/B runs
@@ -1461,9 +1461,9 @@ static int eval_banded(anml_model* m, int want, double* packed, cudaStream_t st)
     {                                                                                                               \
         if (bulk) {                                                                                                 \
             static ConfiguredOn configured;                                                                         \
-            if ((E) && !configured.has(m->device)) {                                                                \
+            if (!configured.has(m->device)) {                                                                       \
                 CU_TRY(cudaFuncSetAttribute(spline_banded_bulk_kernel<D, H, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                            (int)(BULK_STAGES * 5 * BULK_ROWS * sizeof(double))));                  \
+                                            (int)(BULK_STAGES * ((E) ? 5 * BULK_ROWS_EXTRAS : 2 * BULK_ROWS_PLAIN) * sizeof(double)))); \
                 configured.set(m->device);                                                                          \
             }                                                                                                       \
             spline_banded_bulk_kernel<D, H, E><<<b.grid, 256, bulk_smem, st>>>(a);                                  \

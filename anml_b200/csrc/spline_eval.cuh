@@ -224,20 +224,30 @@ __global__ void __launch_bounds__(256, EXTRAS ? 2 : ANML_BANDED_MINB) spline_ban
 // outstanding bytes to saturate HBM (ncu: DRAM 56 % busy, long-scoreboard stalls 5.2 per issue), and a
 // deeper register prefetch costs the occupancy it needs (profiles/r2_ab_banded.txt).  Here thread 0 of
 // the CTA streams the CTA's slice in chunks of BULK_ROWS rows per vector with cp.async.bulk (the TMA
-// engine, completion on an mbarrier) into a ring of BULK_STAGES stages: (stages - 1) x vectors x 4 KB in
-// flight per CTA whatever the register budget, and every thread reads its two rows of a chunk with one
-// 16-byte shared-memory load per vector.  Runs of constant knot interval are walked inside the chunk
-// loop: a chunk that holds a run boundary is simply visited by both runs.
-constexpr int BULK_ROWS = 512;   // per chunk and vector: 4 KB
-constexpr int BULK_STAGES = 4;
+// engine, completion on an mbarrier) into a ring of BULK_STAGES stages: (stages - 1) x vectors x 8 KB in
+// flight per CTA whatever the register budget; every thread pulls its four rows of a chunk into
+// registers with two 16-byte shared-memory loads per vector, and its warp releases the stage at once
+// (mbarrier `empty`, one arrival per warp): no CTA-wide barrier in the chunk loop.  Runs of constant knot
+// interval are walked inside the chunk loop: a chunk that holds a run boundary is visited by both runs.
+#ifndef ANML_BULK_ROWS_PLAIN
+#define ANML_BULK_ROWS_PLAIN 1024
+#endif
+constexpr int BULK_ROWS_PLAIN = ANML_BULK_ROWS_PLAIN;  // rows per chunk and vector without / with extra row vectors
+constexpr int BULK_ROWS_EXTRAS = 1024;                 // (8 KB per vector: four rows per thread)
+constexpr int BULK_STAGES = 3;
 
+#ifndef ANML_BULK_MINB
+#define ANML_BULK_MINB 2  // the copies, not the warps, hide the HBM latency here: registers matter more than occupancy
+#endif
 template <int DEG, bool HESS, bool EXTRAS>
-__global__ void __launch_bounds__(256, EXTRAS ? 2 : 3) spline_banded_bulk_kernel(const BandedArgs a) {
+__global__ void __launch_bounds__(256, EXTRAS ? 2 : ANML_BULK_MINB) spline_banded_bulk_kernel(const BandedArgs a) {
     using C = BandedCfg<DEG>;
     constexpr int NG = C::NG, NH = C::NH, NM = C::NM;
+    constexpr int BULK_ROWS = EXTRAS ? BULK_ROWS_EXTRAS : BULK_ROWS_PLAIN;
+    constexpr int NPAIR = BULK_ROWS / 512;  // 16-byte row pairs per thread and chunk
     extern __shared__ __align__(128) unsigned char bulk_smem[];
     __shared__ double red[8][NM + 1];
-    __shared__ __align__(8) unsigned long long full_bar[BULK_STAGES];
+    __shared__ __align__(8) unsigned long long bar_mem[2 * BULK_STAGES];  // full[stage] (tx bytes), empty[stage] (8 warps)
     const int nint = a.nk - 1;
     const int rec = nint * NM + 1;
     double* out = a.partials + (size_t)blockIdx.x * rec;
@@ -256,24 +266,27 @@ __global__ void __launch_bounds__(256, EXTRAS ? 2 : 3) spline_banded_bulk_kernel
     if (has_wt) { i_wt = nv; vec[nv++] = a.weights; }
     const uint32_t stage_bytes = (uint32_t)nv * BULK_ROWS * 8;
     const uint32_t ring = smem_u32(bulk_smem);
-    const uint32_t bars = smem_u32(full_bar);
-    const long long nchunks = lo < hi ? (hi - lo + BULK_ROWS - 1) / BULK_ROWS : 0;
+    const uint32_t full = smem_u32(bar_mem), empty = full + BULK_STAGES * 8;
+    const int nchunks = lo < hi ? (int)((hi - lo + BULK_ROWS - 1) / BULK_ROWS) : 0;
 
-    auto issue = [&](long long c) {  // thread 0: chunk c -> stage c % BULK_STAGES
-        const int s = (int)(c % BULK_STAGES);
-        const long long cs = lo + c * BULK_ROWS;
+    auto issue = [&](int c) {  // thread 0: chunk c -> stage c % BULK_STAGES
+        const int s = c % BULK_STAGES;
+        const long long cs = lo + (long long)c * BULK_ROWS;
         long long rows = hi - cs < BULK_ROWS ? hi - cs : BULK_ROWS;
         rows += rows & 1;  // 16-byte granules; the arrays carry two spare doubles
         const uint32_t bytes = (uint32_t)rows * 8;
-        mbar_arrive_expect_tx(bars + s * 8, bytes * nv);
+        mbar_arrive_expect_tx(full + s * 8, bytes * nv);
 #pragma unroll
         for (int v = 0; v < 5; ++v)
-            if (v < nv) bulk_load_1d(ring + s * stage_bytes + v * BULK_ROWS * 8, vec[v] + cs, bytes, bars + s * 8);
+            if (v < nv) bulk_load_1d(ring + s * stage_bytes + v * BULK_ROWS * 8, vec[v] + cs, bytes, full + s * 8);
     };
     if (threadIdx.x == 0) {
-        for (int s = 0; s < BULK_STAGES; ++s) mbar_init(bars + s * 8, 1);
+        for (int s = 0; s < BULK_STAGES; ++s) {
+            mbar_init(full + s * 8, 1);
+            mbar_init(empty + s * 8, 8);
+        }
         mbar_fence_init();
-        for (long long c = 0; c < nchunks && c < BULK_STAGES; ++c) issue(c);
+        for (int c = 0; c < nchunks && c < BULK_STAGES - 1; ++c) issue(c);
     }
     double objacc = 0.0;
     bool bad_domain = false;
@@ -284,8 +297,11 @@ __global__ void __launch_bounds__(256, EXTRAS ? 2 : 3) spline_banded_bulk_kernel
         while (k < nint - 1 && a.seg[k + 1] <= lo) ++k;
     }
     double knot = 0.0, d[DEG + 1], G[NG], M[NH];
+    long long run_end = hi;
     auto begin_run = [&]() {
         knot = a.knots[k];
+        const long long e = a.seg[k + 1];
+        run_end = e < hi ? e : hi;
 #pragma unroll
         for (int j = 0; j <= DEG; ++j) {
             double s = 0.0;
@@ -348,37 +364,66 @@ __global__ void __launch_bounds__(256, EXTRAS ? 2 : 3) spline_banded_bulk_kernel
     };
 
     if (lo < hi) begin_run();
-    for (long long c = 0; c < nchunks; ++c) {
-        const int s = (int)(c % BULK_STAGES);
-        mbar_wait(bars + s * 8, (uint32_t)((c / BULK_STAGES) & 1));
-        const long long cs = lo + c * BULK_ROWS;
-        const long long ce = cs + BULK_ROWS < hi ? cs + BULK_ROWS : hi;
-        // this thread's two rows of the chunk
-        const uint32_t at = ring + s * stage_bytes + threadIdx.x * 16;
-        const double2 x2 = lds128(at), ob2 = lds128(at + BULK_ROWS * 8);
-        double2 se2 = make_double2(1.0, 1.0), of2 = make_double2(0.0, 0.0), wt2 = make_double2(1.0, 1.0);
-        if (EXTRAS) {
-            if (has_se) se2 = lds128(at + i_se * BULK_ROWS * 8);
-            if (has_off) of2 = lds128(at + i_off * BULK_ROWS * 8);
-            if (has_wt) wt2 = lds128(at + i_wt * BULK_ROWS * 8);
+    for (int c = 0; c < nchunks; ++c) {
+        const int s = c % BULK_STAGES;
+        // keep BULK_STAGES - 1 chunks in flight: the stage of chunk c - 1 is refilled once all 8 warps left it
+        if (threadIdx.x == 0 && c + BULK_STAGES - 1 < nchunks) {
+            if (c > 0) mbar_wait(empty + ((c - 1) % BULK_STAGES) * 8, (uint32_t)(((c - 1) / BULK_STAGES) & 1));
+            issue(c + BULK_STAGES - 1);
         }
-        const long long r0 = cs + 2 * threadIdx.x;
-        long long pos = cs;
-        while (pos < ce) {
-            long long run_end = a.seg[k + 1] < hi ? a.seg[k + 1] : hi;
-            const long long stop = ce < run_end ? ce : run_end;
-            if (r0 >= pos && r0 < stop) row(x2.x, ob2.x, se2.x, of2.x, wt2.x);
-            if (r0 + 1 >= pos && r0 + 1 < stop) row(x2.y, ob2.y, se2.y, of2.y, wt2.y);
-            pos = stop;
-            if (pos == run_end && pos < hi) {  // the run ends inside (or at the end of) this chunk
-                end_run();
-                ++k;
-                while (k < nint - 1 && a.seg[k + 1] <= pos) ++k;  // empty intervals (repeated knots)
-                begin_run();
+        mbar_wait(full + s * 8, (uint32_t)((c / BULK_STAGES) & 1));
+        const long long cs = lo + (long long)c * BULK_ROWS;
+        const long long ce = cs + BULK_ROWS < hi ? cs + BULK_ROWS : hi;
+        // this thread's rows of the chunk: NPAIR pairs, 512 rows apart (coalesced 16-byte shared-memory loads)
+        const uint32_t at = ring + s * stage_bytes + threadIdx.x * 16;
+        double2 x2[NPAIR], ob2[NPAIR], se2[NPAIR], of2[NPAIR], wt2[NPAIR];
+#pragma unroll
+        for (int h = 0; h < NPAIR; ++h) {
+            x2[h] = lds128(at + h * 4096);
+            ob2[h] = lds128(at + h * 4096 + BULK_ROWS * 8);
+            se2[h] = make_double2(1.0, 1.0); of2[h] = make_double2(0.0, 0.0); wt2[h] = make_double2(1.0, 1.0);
+            if (EXTRAS) {
+                if (has_se) se2[h] = lds128(at + h * 4096 + i_se * BULK_ROWS * 8);
+                if (has_off) of2[h] = lds128(at + h * 4096 + i_off * BULK_ROWS * 8);
+                if (has_wt) wt2[h] = lds128(at + h * 4096 + i_wt * BULK_ROWS * 8);
             }
         }
-        __syncthreads();  // every thread has read the stage
-        if (threadIdx.x == 0 && c + BULK_STAGES < nchunks) issue(c + BULK_STAGES);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s * 8);  // this warp holds its rows in registers: the stage may be refilled
+        const long long r0 = cs + 2 * threadIdx.x;
+        if (ce <= run_end) {
+            // common case: the whole chunk lies in the current run
+#pragma unroll
+            for (int h = 0; h < NPAIR; ++h) {
+                const long long r = r0 + 512 * h;
+                if (r < ce) row(x2[h].x, ob2[h].x, se2[h].x, of2[h].x, wt2[h].x);
+                if (r + 1 < ce) row(x2[h].y, ob2[h].y, se2[h].y, of2[h].y, wt2[h].y);
+            }
+        } else {
+            long long pos = cs;
+            while (pos < ce) {
+                const long long stop = ce < run_end ? ce : run_end;
+#pragma unroll
+                for (int h = 0; h < NPAIR; ++h) {
+                    const long long r = r0 + 512 * h;
+                    if (r >= pos && r < stop) row(x2[h].x, ob2[h].x, se2[h].x, of2[h].x, wt2[h].x);
+                    if (r + 1 >= pos && r + 1 < stop) row(x2[h].y, ob2[h].y, se2[h].y, of2[h].y, wt2[h].y);
+                }
+                pos = stop;
+                if (pos == run_end && pos < hi) {  // the run ends inside this chunk
+                    end_run();
+                    ++k;
+                    while (k < nint - 1 && a.seg[k + 1] <= pos) ++k;  // empty intervals (repeated knots)
+                    begin_run();
+                }
+            }
+        }
+        if (ce == run_end && ce < hi) {  // the run ends exactly at the chunk's end
+            end_run();
+            ++k;
+            while (k < nint - 1 && a.seg[k + 1] <= ce) ++k;
+            begin_run();
+        }
     }
     if (lo < hi) end_run();
     objacc = warp_sum(objacc);
