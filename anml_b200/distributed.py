@@ -139,11 +139,20 @@ class ShmMailbox:
         import time
 
         want = self.seq + 1.0
+        buf = self.buf
+        t0 = None
         spins = 0
-        while self.buf[0] < want:
+        while buf[0] < want:
             spins += 1
-            if spins > 20000:  # ~ms of idling: stop burning the core while the solver thinks
-                time.sleep(0.0002)
+            if (spins & 1023) == 0:
+                # an evaluation takes 0.1-500 ms and the next post follows it at once, so keep polling hot for a
+                # long while (a sleeping poller adds its sleep quantum to EVERY rank's step: the all-reduce waits
+                # for the slowest); only a solver that thinks for more than 2 s gets the core back
+                now = time.perf_counter()
+                if t0 is None:
+                    t0 = now
+                elif now - t0 > 2.0:
+                    time.sleep(0.0005)
         self.seq = want
         return float(self.buf[1]), self.buf[2:].copy()
 
