@@ -317,6 +317,12 @@ class ShardedModel:
         obj = float(host[0])
         grad = host[1: 1 + P].copy()
         hess = host[1 + P: 1 + P + P * P].reshape(P, P).copy() if hessian else None
+        if hess is not None and self.world > 1 and self._peer is None and self._on_gpu:
+            # NCCL may add the ranks' contributions to (i, j) and (j, i) in different orders (different
+            # chunks of its ring / tree): mirror the lower triangle so that the Hessian stays exactly
+            # symmetric, as the peer-memory kernel (fixed rank order) and the single-GPU path deliver it
+            il = np.tril_indices(P, -1)
+            hess.T[il] = hess[il]
         return obj, grad, hess
 
     # ---- rank-0 driver / worker loop ---------------------------------------------------
