@@ -115,6 +115,27 @@ def main():
             assert np.abs(sh - sw[2]).max() <= 1e-9 * np.abs(sw[2]).max()
             ssh.close()
 
+        # ---- a wide design (P = 260: the packed record exceeds the peer window's 512 KB limit) goes through NCCL;
+        # the Hessian must come back exactly symmetric all the same
+        pw = 260
+        Xw = rng.normal(size=(6000, pw)) / np.sqrt(pw / 8.0)
+        Xw[:, 0] = 1.0
+        bw = rng.normal(size=pw) * 0.2
+        ow = (rng.uniform(size=6000) < 1 / (1 + np.exp(-Xw @ bw))).astype(float)
+        wlo, whi = shard_rows(6000, world, rank)
+        wdf = pd.DataFrame({f"c{j}": Xw[wlo:whi, j] for j in range(1, pw)})
+        wdf["obs"] = ow[wlo:whi]
+        wvars = [Variable(Component("intercept", default_value=1.0))] + [Variable(f"c{j}") for j in range(1, pw)]
+        wmodel = Model("binomial", DataExample("obs", "obs_se"), [Parameter(wvars, transform=Expit(), device=local_rank)], device=local_rank)
+        wmodel.attach(wdf)
+        wsh = ShardedModel(NativeLocalEvaluator(wmodel, torch.device("cuda", local_rank)))
+        assert wsh._peer is None  # 2 + P + P^2 = 67862 doubles > 65536
+        wo, wg, wh = wsh.unpack(wsh.evaluate_collective(0.5 * bw, True))
+        ww = O.model_eval_fused("binomial", ow, [Xw], ["expit"], 0.5 * bw)
+        assert abs(wo - ww[0]) <= 1e-10 * abs(ww[0]) and np.abs(wg - ww[1]).max() <= 1e-10 * np.abs(ww[1]).max()
+        assert np.abs(wh - ww[2]).max() <= 1e-9 * np.abs(ww[2]).max() and np.array_equal(wh, wh.T)
+        wsh.close()
+
         res = sharded.fit(np.zeros(p), options={"gtol": 1e-10})
         if rank == 0:
             from scipy.optimize import minimize
