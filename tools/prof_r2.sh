@@ -6,18 +6,18 @@ run_plain() { "$@" > gpurun_out/plain.log 2>&1 || { echo "plain run failed: $*";
 
 # 1. north star shape at 1e7 rows: launch list + full capture of the Hessian kernel and of the gradient pass
 run_plain $B --rows 1e7 && {
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:anml -c 400 --csv --log-file gpurun_out/r2_launches_bench_rows1e7.csv $B --rows 1e7 > gpurun_out/ncu1.log 2>&1
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:fused_|finish_|banded_|wide_|comm_|linpred|rowterms|xtr_" -c 400 --csv --log-file gpurun_out/r2_launches_bench_rows1e7.csv $B --rows 1e7 > gpurun_out/ncu1.log 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused_hess -s 4 -c 1 -o gpurun_out/r2_fused_hess $B --rows 1e7 > gpurun_out/ncu2.log 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:finish_fused -s 4 -c 1 -o gpurun_out/r2_finish $B --rows 1e7 > gpurun_out/ncu2b.log 2>&1
 }
 # 2. config 3 (banded spline evaluator), full size
 run_plain $B --config c3 && {
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:anml -c 400 --csv --log-file gpurun_out/r2_launches_bench_c3.csv $B --config c3 > gpurun_out/ncu3.log 2>&1
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:spline_banded -s 3 -c 1 -o gpurun_out/r2_spline_banded $B --config c3 > gpurun_out/ncu4.log 2>&1
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:fused_|finish_|banded_|wide_|comm_|linpred|rowterms|xtr_" -c 400 --csv --log-file gpurun_out/r2_launches_bench_c3.csv $B --config c3 > gpurun_out/ncu3.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:spline_banded -s 3 -c 1 -o gpurun_out/r2_spline_banded_bulk $B --config c3 > gpurun_out/ncu4.log 2>&1
 }
 # 3. config 4 at 1e7 rows: the three Hessian launches of one evaluation (MODE 3, MODE 1, MODE 1)
 run_plain $B --config c4 --rows 1e7 && {
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:anml -c 400 --csv --log-file gpurun_out/r2_launches_bench_c4_rows1e7.csv $B --config c4 --rows 1e7 > gpurun_out/ncu5.log 2>&1
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:fused_|finish_|banded_|wide_|comm_|linpred|rowterms|xtr_" -c 400 --csv --log-file gpurun_out/r2_launches_bench_c4_rows1e7.csv $B --config c4 --rows 1e7 > gpurun_out/ncu5.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:fused_hess -s 6 -c 3 -o gpurun_out/r2_fused_hess_c4 $B --config c4 --rows 1e7 > gpurun_out/ncu6.log 2>&1
 }
 # gpurun brings back at most 64 MiB: keep the metric extracts (and the raw pages), drop the reports
