@@ -19,6 +19,7 @@
 #include "fused_eval.cuh"
 #include "finish.cuh"
 #include "fused_hess.cuh"
+#include "fused_hess_i8.cuh"
 #include "generic.cuh"
 #include "spline.cuh"
 #include "spline_eval.cuh"
@@ -80,6 +81,7 @@ struct anml_design {
     CUtensorMap tmap3d64;  // box 16 x 64 x p/16
     bool has64 = false, has3d64 = false;
     int sm_count = 0;
+    unsigned long long version = 0;  // bumped whenever the library rewrites X (column maxima cached by a model go stale)
     // deferred build (anml_design_create_deferred): X is allocated, and the recorded spline blocks are
     // evaluated, the first time something needs the dense matrix.  A one-spline model on the banded
     // evaluator never does, so BASELINE config #3 no longer carries an 8.8 GB design it does not read.
@@ -127,6 +129,18 @@ struct anml_model {
     bool prior_enabled = true;
     bool force_generic = false, no_fast = false, no_specialise = false, banded_registers = false;
     bool force_signed = false;
+    bool no_i8 = false;  // option "hess_i8" = 0: keep the Hessian of 64-column logistic / Gaussian models on DMMA
+    // INT8-tensor-core Hessian (fused_hess_i8.cuh): column scales of the design they were taken from, flush scratch
+    struct I8State {
+        const anml_design* design = nullptr;
+        const double* X = nullptr;
+        long long n = 0;
+        unsigned long long version = 0;
+        bool usable = false;
+        double* cs = nullptr;                 // [64] scales | [64] reciprocals
+        unsigned long long* colmax = nullptr; // [64] bit patterns of the column maxima
+        double* scratch = nullptr;            // [sm_count][128][64]
+    } i8;
     cudaStream_t stream = nullptr;
     int sm_count = 0;
     // evaluation buffers (allocated by ensure_buffers once P is known)
@@ -451,6 +465,7 @@ extern "C" int anml_design_set_columns(anml_design* d, int col0, int ncols, cons
     if (d->n == 0) return ANML_OK;
     CU_TRY(cudaSetDevice(d->device));
     TRY(design_materialize(d));
+    d->version++;
     if (src_on_device) {
         scatter_columns_kernel<<<grid_for(d->n * ncols, 256, d->sm_count), 256>>>(d->X, d->n, d->ld, col0, ncols, src, src_ld);
         CU_TRY(cudaGetLastError());
@@ -668,6 +683,7 @@ extern "C" int anml_design_set_spline(anml_design* d, int col0, const double* x,
     if (!d || !x || !knots) return fail(ANML_EINVAL, "anml_design_set_spline: NULL argument");
     const int nb = n_knots - 1 + degree;
     if (col0 < 0 || col0 + nb > d->p) return fail(ANML_EINVAL, "anml_design_set_spline: %d basis columns at %d do not fit a %d-column design", nb, col0, d->p);
+    d->version++;
     CU_TRY(cudaSetDevice(d->device));
     if (d->deferred && !d->X && x_on_device && !interval_out) {
         // record the block; it is evaluated if and when the dense matrix is needed (design_materialize)
@@ -897,6 +913,9 @@ extern "C" int anml_model_destroy(anml_model* m) {
     cudaSetDevice(m->device);
     (void)model_quiesce(m);
     if (m->eval_done) cudaEventDestroy(m->eval_done);
+    if (m->i8.cs) cudaFree(m->i8.cs);
+    if (m->i8.colmax) cudaFree(m->i8.colmax);
+    if (m->i8.scratch) cudaFree(m->i8.scratch);
     free_eval_buffers(m);
     free_banded(m);
     for (int k = 0; k < 2; ++k) free_prior(m->par[k].prior);
@@ -1038,6 +1057,8 @@ extern "C" int anml_model_set_option(anml_model* m, const char* name, int64_t va
     else if (!strcmp(name, "no_warp_specialisation")) m->no_specialise = value != 0;
     else if (!strcmp(name, "force_signed_weights")) m->force_signed = value != 0;
     else if (!strcmp(name, "banded_register_prefetch")) m->banded_registers = value != 0;
+    else if (!strcmp(name, "hess_i8")) m->no_i8 = value == 0;
+    else if (!strcmp(name, "hess_i8_rescan")) m->i8.design = nullptr;
     else return fail(ANML_EINVAL, "unknown option '%s'", name);
     return ANML_OK;
 }
@@ -1326,6 +1347,82 @@ static int run_fused_block(anml_model* m, const anml_design* d, FusedArgs a, boo
     m->main_launches += 1;
     m->all_launches += 1;
     return launch_finish(m, grid, nb16, hess, d->p, plan, packed, st);
+}
+
+// ---- Hessian on the INT8 tensor cores (fused_hess_i8.cuh) -------------------------------------------------
+// One-parameter models whose sqrt(w) has a bound known in advance: canonical logistic (w <= 1/4) and the
+// Gaussian identity model with unit obs_se (w = 1).  64 columns, dense row pitch, no per-row weights.
+static bool i8_eligible(const anml_model* m, const anml_design* d, bool hess) {
+    if (!hess || m->no_i8 || m->no_fast || m->no_specialise || m->force_signed || m->force_generic) return false;
+    if (m->K != 1 || d->p != 64 || d->ld != 64 || !d->has3d || m->weights) return false;
+    if (const char* s = getenv("ANML_B200_HESS_I8"))
+        if (s[0] == '0') return false;
+    const int link = m->par[0].link;
+    if (m->family == ANML_FAMILY_BINOMIAL && link == ANML_LINK_EXPIT) return true;
+    if (m->family == ANML_FAMILY_GAUSSIAN && link == ANML_LINK_IDENTITY && !m->se) return true;
+    return false;
+}
+
+// column scales cs_j = 2^-(e_j + 1), 2^(e_j - 1) <= max_i |x_ij| < 2^(e_j): |x cs| < 1/2.  One pass over X, once per
+// design (and again after the library rewrote it).  A NaN or infinite column keeps the model on the DMMA path.
+static int i8_prepare(anml_model* m, const anml_design* d, cudaStream_t st) {
+    anml_model::I8State& s = m->i8;
+    if (s.design == d && s.X == d->X && s.n == d->n && s.version == d->version) return ANML_OK;
+    if (!s.cs) CU_TRY(cudaMalloc(&s.cs, 128 * sizeof(double)));
+    if (!s.colmax) CU_TRY(cudaMalloc(&s.colmax, 64 * sizeof(unsigned long long)));
+    if (!s.scratch) CU_TRY(cudaMalloc(&s.scratch, (size_t)m->sm_count * 4 * 64 * 64 * sizeof(double)));
+    CU_TRY(cudaMemsetAsync(s.colmax, 0, 64 * sizeof(unsigned long long), st));
+    colmax64_kernel<<<m->sm_count * 4, 256, 0, st>>>(d->X, d->n, d->ld, s.colmax);
+    CU_TRY(cudaGetLastError());
+    unsigned long long bits[64];
+    CU_TRY(cudaMemcpyAsync(bits, s.colmax, sizeof(bits), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    double cs[128];
+    bool ok = true;
+    for (int j = 0; j < 64; ++j) {
+        double mx;
+        memcpy(&mx, &bits[j], sizeof(double));
+        if (!std::isfinite(mx)) ok = false;
+        int e = 0;
+        if (ok && mx > 0.0) (void)std::frexp(mx, &e);  // mx = f 2^e, f in [1/2, 1)
+        cs[j] = (ok && mx > 0.0) ? std::ldexp(1.0, -(e + 1)) : 1.0;
+        cs[64 + j] = 1.0 / cs[j];
+    }
+    CU_TRY(cudaMemcpyAsync(s.cs, cs, sizeof(cs), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    s.design = d; s.X = d->X; s.n = d->n; s.version = d->version; s.usable = ok;
+    m->all_launches += 1;
+    return ANML_OK;
+}
+
+static int run_fused_i8(anml_model* m, const anml_design* d, FusedArgs a, const FinishPlan& plan, double* packed, cudaStream_t st) {
+    using C = I8Cfg;
+    static ConfiguredOn configured;
+    auto kern = fused_hess_i8_kernel;
+    if (!configured.has(d->device)) {
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        configured.set(d->device);
+    }
+    const long long nblk = (d->n + 31) / 32;
+    int grid = nblk < m->sm_count ? (int)nblk : m->sm_count;
+    if (grid < 1) grid = 1;
+    a.partials = m->d_partials;
+    a.status = m->d_status;
+    I8Extra x;
+    x.cs = m->i8.cs; x.scratch = m->i8.scratch;
+    // sqrt(w) sv_scale <= 1/2: the logistic weight is at most 1/4; the unit-variance Gaussian has sqrt(w) = 1
+    x.sv_scale = (m->family == ANML_FAMILY_BINOMIAL) ? 1.0 : 0.5;
+    x.out_scale = 1.0 / (x.sv_scale * x.sv_scale);
+    EventPair* ep = next_events(m);
+    if (ep) CU_TRY(cudaEventRecord(ep->a, st));
+    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(d->tmap3d, a, x);
+    CU_TRY(cudaGetLastError());
+    if (ep) CU_TRY(cudaEventRecord(ep->b, st));
+    snprintf(g_kernel, sizeof(g_kernel), "fused_hess_i8_kernel");
+    m->main_kernel = g_kernel;
+    m->main_launches += 1;
+    m->all_launches += 1;
+    return launch_finish(m, grid, 4, true, d->p, plan, packed, st);
 }
 
 // Gaussian prior terms as a separate launch: only the paths whose epilogue is not the fused one
@@ -1635,7 +1732,13 @@ static int eval_on_stream(anml_model* m, const double* x_host, int want, double*
         a.beta = m->d_beta + m->par[0].pad_off; a.obs = m->obs; a.se = m->se; a.offset = m->par[0].offset; a.weights = m->weights;
         FinishPlan plan;
         plan.write_flag = true; plan.prior_k = 0; plan.prior_obj = true;
-        TRY(run_fused_block(m, d0, a, hess, 0, plan, packed, true, st));
+        bool i8 = i8_eligible(m, d0, hess);
+        if (i8) {
+            TRY(i8_prepare(m, d0, st));
+            i8 = m->i8.usable;
+        }
+        if (i8) TRY(run_fused_i8(m, d0, a, plan, packed, st));
+        else TRY(run_fused_block(m, d0, a, hess, 0, plan, packed, true, st));
     } else {
         TRY(eval_general(m, want, packed, st));
     }
@@ -1792,6 +1895,11 @@ extern "C" int anml_model_eval(anml_model* m, const double* x_host, int want, do
     }
     CU_TRY(cudaStreamSynchronize(m->stream));
     m->eval_pending = false;
+    if (m->h_packed[flag_at] >= 1024.0) {
+        m->i8.design = nullptr;  // rescan the column maxima at the next evaluation
+        return fail(ANML_ESTATE, "design values outside the column ranges recorded for the INT8 Hessian path (was a wrapped matrix rewritten in place?); "
+                                 "the ranges are taken again at the next evaluation");
+    }
     if (m->h_packed[flag_at] != 0.0) return fail(ANML_EDOMAIN, "linear predictor outside the domain of a Log/Logit mapping");
     if (want & ANML_WANT_OBJ) *obj = m->h_packed[0];
     if (want & ANML_WANT_GRAD) memcpy(grad, m->h_packed + 1, P * sizeof(double));

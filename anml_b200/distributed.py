@@ -192,6 +192,10 @@ class NativeLocalEvaluator:
     def stream_ptr(self) -> int:
         return self.torch.cuda.current_stream(self.device).cuda_stream or 1
 
+    def rescan_ranges(self):
+        """Forget the column ranges of the INT8 Hessian path (taken again at the next evaluation)."""
+        self.model.native.set_option("hess_i8_rescan", 1)
+
 
 class ShardedModel:
     """objective / gradient / hessian of a row-sharded model.
@@ -312,6 +316,11 @@ class ShardedModel:
             host = np.asarray(packed)
         if self._peer is not None and host[0] != host[0]:
             self._peer.check()  # NaN objective: a peer may have missed the all-reduce (timeout)
+        if host[1 + P + P * P] >= 1024.0:  # (summed over ranks: the INT8 Hessian path's range flag, csrc/fused_hess_i8.cuh)
+            if hasattr(self.local, "rescan_ranges"):
+                self.local.rescan_ranges()
+            raise RuntimeError("design values outside the column ranges recorded for the INT8 Hessian path (was a wrapped "
+                               "matrix rewritten in place?); the ranges are taken again at the next evaluation")
         if host[1 + P + P * P] != 0.0:
             raise ValueError("linear predictor outside the domain of a Log/Logit mapping")
         obj = float(host[0])

@@ -729,6 +729,23 @@ def run_gpu(args, cfg):
         grad_kernel = model.native.main_kernel()
         (grad_kernel_ms,) = max_over_ranks([g_ms / max(g_launches, 1)])
 
+    # ---- the same evaluation with the Hessian kept on the FP64 tensor cores (DMMA): the INT8 path's reference point
+    dmma_kernel_ms, dmma_kernel = None, None
+    if main_kernel.startswith("fused_hess_i8"):
+        model.native.set_option("hess_i8", 0)
+        for k in range(2):
+            sharded.evaluate_collective(xs[k], True)
+        barrier()
+        model.native.kernel_time(reset=True)
+        dsteps = max(3, min(steps, 10))
+        for k in range(dsteps):
+            sharded.evaluate_collective(xs[warmup + (k % steps)], True)
+        barrier()
+        d_ms, d_launches, _ = model.native.kernel_time(reset=True)
+        dmma_kernel = model.native.main_kernel()
+        (dmma_kernel_ms,) = max_over_ranks([d_ms / max(d_launches, 1)])
+        model.native.set_option("hess_i8", 1)
+
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
 
     # ---- the collective alone (N > 1): the peer-memory kernel and, beside it, NCCL on the same record
@@ -776,6 +793,28 @@ def run_gpu(args, cfg):
             roofline = {"kernel": main_kernel, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                         "traffic": None if traffic_row is None else traffic_row * n, "kernel_ms": kernel_ms, "bytes_per_launch": bytes_alg,
                         "algorithmic": "8 B (x) + 8 B (obs) per row", "peak_source": hbm_src, "traffic_source": traffic_src}
+        elif main_kernel.startswith("fused_hess_i8"):
+            # Hessian on the INT8 tensor cores (csrc/fused_hess_i8.cuh): the pass is bounded by reading X once
+            bytes_alg = 8.0 * n * p + 8.0 * n
+            achieved = bytes_alg / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+            traffic_row, traffic_src = ncu_traffic([main_kernel])
+            int8_macs = 98304.0 * n  # four tcgen05.mma per 32-row block: M=128 x (N=256 + 128 + 256 + 128) x K=32
+            roofline = {"kernel": main_kernel, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                        "traffic": None if traffic_row is None else traffic_row * n, "kernel_ms": kernel_ms, "bytes_per_launch": bytes_alg,
+                        "launches_per_step": launches_per_step,
+                        "algorithmic": "8 B x (p + 1) per row: X read once, obs",
+                        "peak_source": hbm_src, "traffic_source": traffic_src,
+                        "hessian": "X^T diag(w) X rebuilt exactly from six int8 digit planes of sqrt(w) x (Ozaki splitting): tcgen05.mma kind::i8, "
+                                   "int32 accumulators in TMEM, FP64 flush every 32768 rows",
+                        "int8_tensor_tops": 2.0 * int8_macs / (kernel_ms * 1e-3) / 1e12 if kernel_ms > 0 else 0.0,
+                        "fp64_equivalent_tflops": flops / (kernel_ms * 1e-3) / 1e12 if kernel_ms > 0 else 0.0}
+            if dmma_kernel_ms:
+                ach = flops / (dmma_kernel_ms * 1e-3) / 1e12
+                roofline["dmma_path"] = {"kernel": dmma_kernel, "bound": "tensor", "kernel_ms": dmma_kernel_ms, "achieved": ach, "peak": peak_tf,
+                                         "unit": "TFLOP/s", "frac": ach / peak_tf, "peak_dmma_microbench": dmma_peak,
+                                         "frac_of_dmma_microbench": ach / dmma_peak,
+                                         "note": "same evaluation with option hess_i8 = 0 (Hessian on the FP64 tensor cores, csrc/fused_hess.cuh), "
+                                                 "SYRK convention n*p*(p+1); peak = cuBLAS DGEMM 4096^3 measured in this run"}
         else:
             achieved = flops / (kernel_ms * 1e-3) / 1e12 if kernel_ms > 0 else 0.0
             if kind == "meanvar":

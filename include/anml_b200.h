@@ -171,6 +171,20 @@ int anml_model_kernel_time(anml_model* m, int reset, double* total_ms, int64_t* 
 /* name and template arguments of the kernel that anml_model_kernel_time last timed, e.g.
  * "fused_hess_kernel<4, 2, 0, 0, 1, 32>" (bench.py looks its ncu DRAM traffic up under that key) */
 int anml_model_main_kernel(const anml_model* m, char* out, int out_len);
+/* Evaluation switches (all default 0 unless noted; development / A-B use, results stay within tolerance either way):
+ *   "hess_i8" (default 1)       Hessian of an eligible model (one parameter, exactly 64 dense columns, binomial/expit or
+ *                               unit-variance gaussian/identity, no per-row weights) on the INT8 tensor cores
+ *                               (csrc/fused_hess_i8.cuh); 0 keeps it on the FP64 tensor cores (DMMA).  Environment
+ *                               ANML_B200_HESS_I8=0 switches it off for the whole process.
+ *   "hess_i8_rescan"            forget the per-column value ranges the INT8 path recorded for the design (taken again at
+ *                               the next evaluation); needed only after rewriting a WRAPPED device matrix in place --
+ *                               an evaluation that meets a value outside the recorded range fails with ANML_ESTATE
+ *                               rather than returning a wrong Hessian, and rescans by itself
+ *   "force_generic"             the general path (linpred / rowterms / xtr / wide_hessian) whatever the model shape
+ *   "no_fast_math_paths"        the reference's literal link / family formulas instead of the canonical-pair shortcuts
+ *   "no_warp_specialisation"    symmetric 8-warp Hessian kernel (fused_eval_kernel<.., true, ..>)
+ *   "force_signed_weights"      sign handling of w < 0 even for canonical pairs
+ *   "banded_register_prefetch"  register-prefetch variant of the banded spline evaluator */
 int anml_model_set_option(anml_model* m, const char* name, int64_t value);
 
 /* ---- row-sharded evaluation: all-reduce of the packed record over peer memory ----

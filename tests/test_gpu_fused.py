@@ -306,3 +306,113 @@ def test_log_and_logit_links_in_a_model(link, general):
     check(got, want)
     with pytest.raises(ValueError):  # outside the domain: the reference raises before computing (:98-99, :148-151)
         gpu_eval("gaussian", X, obs, se, None, link, -beta, options=(("force_generic", general),))
+
+
+# ---------------------------------------------------------------------------------------------
+# Hessian on the INT8 tensor cores (csrc/fused_hess_i8.cuh): 64-column logistic / unit-variance Gaussian models
+# ---------------------------------------------------------------------------------------------
+def i8_model(family, n, seed, scale_cols=False, offset=False, prior=True):
+    from anml_b200 import _native as N
+
+    X, obs, se, off, link, x = make_problem(family, n, 64, seed, with_offset=offset)
+    if scale_cols:  # columns of very different magnitude: the per-column power-of-two scales matter
+        X = X * np.exp2(np.arange(64) % 29 - 14)[None, :]
+        X[:, 0] = 1.0
+        x = x / np.exp2(np.arange(64) % 29 - 14)
+        x[0] *= np.exp2(-14.0)
+    design = N.Design(n, 64)
+    design.set_columns(0, X)
+    off_buf = N.DeviceBuffer(0, off) if off is not None else None
+    model = N.NativeModel(n, family, 1)
+    model.set_param(0, design, N.LINK_CODES[LINK_NAME[link]], off_buf)
+    model.set_obs(obs)
+    pr = None
+    if prior:
+        pr = {"direct": (np.zeros(64), np.full(64, 2.0))}
+        model.set_gaussian_prior(0, *pr["direct"])
+    return model, (X, obs, off, link, x, pr), (design, off_buf)
+
+
+@pytest.mark.parametrize("family", ["binomial", "gaussian"])
+@pytest.mark.parametrize("n", [1, 31, 33, 1000, 20011, 300007])
+def test_i8_hessian_against_oracle_and_dmma(family, n):
+    model, (X, obs, off, link, x, pr), keep = i8_model(family, n, seed=n + 5, offset=(n == 20011))
+    got = model.eval(x)
+    assert model.main_kernel().startswith("fused_hess_i8_kernel"), model.main_kernel()
+    again = model.eval(x)
+    assert got[0] == again[0] and np.array_equal(got[1], again[1]) and np.array_equal(got[2], again[2])
+    want = O.model_eval_fused(family, obs, [X], [link], x, offsets=[off] if off is not None else None, priors=[pr])
+    check(got, want)
+    # against the DMMA path of the same library: same objective / gradient code, Hessian to ~1e-13
+    model.set_option("hess_i8", 0)
+    ref = model.eval(x)
+    assert model.main_kernel().startswith("fused_hess_kernel"), model.main_kernel()
+    assert np.abs(got[2] - ref[2]).max() <= 1e-12 * np.abs(ref[2]).max()
+    assert abs(got[0] - ref[0]) <= 1e-13 * abs(ref[0])
+    assert np.abs(got[1] - ref[1]).max() <= 1e-12 * np.abs(ref[1]).max()
+
+
+def test_i8_hessian_badly_scaled_columns_entrywise():
+    # with per-column scales every entry is accurate relative to sqrt(H_ii H_jj), not only to the largest entry
+    model, (X, obs, off, link, x, pr), keep = i8_model("binomial", 50021, seed=77, scale_cols=True, prior=False)
+    got = model.eval(x)
+    assert model.main_kernel().startswith("fused_hess_i8_kernel")
+    want = O.model_eval_fused("binomial", obs, [X], [link], x)
+    d = np.sqrt(np.diag(want[2]))
+    assert np.abs((got[2] - want[2]) / np.outer(d, d)).max() <= 1e-11
+    assert np.array_equal(got[2], got[2].T)
+
+
+def test_i8_hessian_many_epochs_against_dmma():
+    # more than 1024 blocks per CTA: the int32 accumulators are flushed several times
+    import torch
+
+    from anml_b200 import _native as N
+
+    n = 24_000_017
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    X = torch.randn((n, 64), dtype=torch.float64, device="cuda", generator=g)
+    X[:, 0] = 1.0
+    beta = torch.randn(64, dtype=torch.float64, device="cuda", generator=g) * 0.1
+    obs = (torch.rand(n, dtype=torch.float64, device="cuda", generator=g) < torch.sigmoid(X @ beta)).double()
+    design = N.Design.wrap(X.data_ptr(), n, 64, 64, keepalive=X)
+    model = N.NativeModel(n, "binomial", 1)
+    model.set_param(0, design, N.LINK_CODES["Expit"])
+    model.set_obs(dev_ptr=obs.data_ptr(), keepalive=obs)
+    x = (0.5 * beta).cpu().numpy()
+    got = model.eval(x)
+    assert model.main_kernel().startswith("fused_hess_i8_kernel")
+    model.set_option("hess_i8", 0)
+    ref = model.eval(x)
+    assert np.abs(got[2] - ref[2]).max() <= 1e-12 * np.abs(ref[2]).max()
+    assert np.array_equal(got[2], got[2].T)
+    assert abs(got[0] - ref[0]) <= 1e-11 * abs(ref[0])
+    # a wrapped matrix rewritten in place beyond the recorded column ranges is detected, not silently mis-evaluated
+    # (coefficient 3 set to zero so that the row keeps an ordinary weight: a huge linear predictor would zero it)
+    model.set_option("hess_i8", 1)
+    x = x.copy()
+    x[3] = 0.0
+    X[5, 3] = 1.0e6
+    torch.cuda.synchronize()
+    with pytest.raises((RuntimeError, ValueError)):
+        model.eval(x)
+    got2 = model.eval(x)  # ranges taken again
+    assert model.main_kernel().startswith("fused_hess_i8_kernel")
+    model.set_option("hess_i8", 0)
+    ref2 = model.eval(x)
+    assert np.abs(got2[2] - ref2[2]).max() <= 1e-11 * np.abs(ref2[2]).max()
+
+
+def test_i8_not_used_outside_its_domain():
+    # per-row weights, obs_se, Poisson, p != 64: the DMMA kernel
+    from anml_b200 import _native as N
+
+    X, obs, se, off, link, x = make_problem("gaussian", 5000, 64, 3, with_se=True)
+    got = gpu_eval("gaussian", X, obs, se, None, link, x)
+    want = O.model_eval_fused("gaussian", obs, [X], [link], x, obs_se=se)
+    check(got, want)
+    model, prob, keep = i8_model("binomial", 4000, seed=9)
+    model.set_weights(np.linspace(0.5, 1.5, 4000))
+    model.eval(prob[4])
+    assert model.main_kernel().startswith("fused_hess_kernel")
