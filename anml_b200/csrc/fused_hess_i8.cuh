@@ -10,27 +10,24 @@
 //         x~ = sum_a d_a 2^(-8a),  a = 1..6,  d_a in [-128, 127];
 //     one FMA does the scaling, the rounding and the digit bias: t = fma(x, sqrt(w) cs, 16 + B 2^-48) with
 //     B = 0x808080808080 leaves the biased digits in the low six mantissa bytes of t (digit = byte ^ 0x80);
-//   * the six digit planes of a 32-row block are int8 operands (K-major, 8x16-byte core matrices, no swizzle,
-//     MN index = 64 (a - 1) + column, K = row); four tcgen05.mma (M = 128: two planes stacked, N = 256 / 128,
-//     K = 32) accumulate every digit-plane product with a + b <= 7 (and the three with a + b = 8 that come
-//     for free) into six 64-column TMEM blocks, equal weights 2^-8(a+b) sharing an accumulator:
-//         planes{1,2} x planes{1,2,3,4} -> blocks 0..3      planes{3,4} x planes{1,2,3,4} -> blocks 2..5
-//         planes{1,2} x planes{5,6}     -> blocks 4, 5      planes{5,6} x planes{1,2}     -> blocks 4, 5
-//     block c carries 2^-8(c+2) in TMEM lanes 0..63 and 2^-8(c+3) in lanes 64..127;
-//   * at most three products of magnitude < 2^14 meet in one int32 accumulator per row: every EPOCH = 1024
-//     blocks (32768 rows) the accumulators are flushed, weighted, into an FP64 scratch matrix of the CTA.
-// What is dropped: |x~ - fixed(x~)| <= 2^-49 per element and digit products of weight <= 2^-72 2^14: the
-// Hessian agrees with the DMMA path to ~1e-14 of its largest entry (tests/test_gpu_fused.py), far inside the
-// 1e-9 of BASELINE.json.  Integer sums do not depend on the order: results are bitwise reproducible.
+//   * the six digit planes of a 32-row block are int8 operands (K-major, 8x16-byte core matrices, no swizzle, K = row),
+//     handled as three plane PAIRS {1,2}, {3,4}, {5,6} of 128 operand rows each (2 planes x 64 columns); four
+//     tcgen05.mma (M = N = 128, K = 32) form {1,2}x{1,2}, {1,2}x{3,4}, {1,2}x{5,6} and {3,4}x{3,4} into four
+//     128-column TMEM blocks: entry (m, n) of pair product (pp, pp') carries weight 2^-8(2(pp+pp') + 2 + x_m + x_n)
+//     (x = plane parity inside the pair).  {3,4}x{1,2} and {5,6}x{1,2} are the transposes of two of those and are
+//     added when the record is written; every other digit-plane product has weight <= 2^-64 2^14 and is dropped;
+//   * one product of magnitude <= 2^14 meets an int32 accumulator per row: every EPOCH = 4095 blocks (131040 rows)
+//     the accumulators are flushed, weighted, into an FP64 scratch matrix of the CTA.
+// What is dropped: |x~ - fixed(x~)| <= 2^-49 per element and the products above: the Hessian agrees with the DMMA
+// path to ~1e-14 of its largest entry (tests/test_gpu_fused.py), far inside the 1e-9 of BASELINE.json.  Integer sums
+// do not depend on the order: results are bitwise reproducible.
 //
-// Roles (one persistent CTA per SM, 32 (NHELP + 1) threads):
-//   * helper warps 0..NHELP-1: a warp owns whole 32-row blocks.  It loads the block straight into registers
-//     (32 LDG.128 per lane, fragment layout: lane (g, t) holds columns 16j + 2g, +1 of rows 4s + t), forms
-//     y = X beta (transposing reduction through shared memory: lane l ends up with row l), the link / family
-//     terms of its row (rowmath.cuh), then per column g += r x and the digit planes, 8 bytes per lane,
-//     column and plane, into a stage of the operand ring;
-//   * warp NHELP: one lane issues the four MMAs of every block as its stage fills (mbarrier full[]), commits
-//     them to the stage's empty[] barrier, and closes every epoch.
+// Roles (one persistent CTA per SM, 480 threads, 128 registers):
+//   * 14 helper warps = 7 pairs; a pair owns whole 32-row blocks, each warp 16 rows of them (lanes 16..31 mirror
+//     0..15 while the 16 rows' link / family terms are taken);
+//   * 1 control warp: lane 0 requests blocks by TMA LOOKAHEAD ahead, and as each block's pair reports its digit
+//     planes ready issues the four MMAs and commits them to the buffer's free[] barrier; it closes every epoch.
+// Buffer life, operand layout and the in-place digit write are described above the kernel.
 // The CTA's partial record has the layout of fused_hess_kernel (finish_fused_kernel is the shared epilogue).
 #pragma once
 #include "common.cuh"

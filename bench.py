@@ -798,14 +798,14 @@ def run_gpu(args, cfg):
             bytes_alg = 8.0 * n * p + 8.0 * n
             achieved = bytes_alg / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
             traffic_row, traffic_src = ncu_traffic([main_kernel])
-            int8_macs = 98304.0 * n  # four tcgen05.mma per 32-row block: M=128 x (N=256 + 128 + 256 + 128) x K=32
+            int8_macs = 65536.0 * n  # four tcgen05.mma per 32-row block: M=128 x N=128 x K=32 each
             roofline = {"kernel": main_kernel, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                         "traffic": None if traffic_row is None else traffic_row * n, "kernel_ms": kernel_ms, "bytes_per_launch": bytes_alg,
                         "launches_per_step": launches_per_step,
                         "algorithmic": "8 B x (p + 1) per row: X read once, obs",
                         "peak_source": hbm_src, "traffic_source": traffic_src,
                         "hessian": "X^T diag(w) X rebuilt exactly from six int8 digit planes of sqrt(w) x (Ozaki splitting): tcgen05.mma kind::i8, "
-                                   "int32 accumulators in TMEM, FP64 flush every 32768 rows",
+                                   "int32 accumulators in TMEM, FP64 flush every 131040 rows",
                         "int8_tensor_tops": 2.0 * int8_macs / (kernel_ms * 1e-3) / 1e12 if kernel_ms > 0 else 0.0,
                         "fp64_equivalent_tflops": flops / (kernel_ms * 1e-3) / 1e12 if kernel_ms > 0 else 0.0}
             if dmma_kernel_ms:

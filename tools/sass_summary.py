@@ -8,7 +8,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "anml_b200", "lib", "libanml_b200.so")
-KEYS = ["DMMA", "DFMA", "DMUL", "DADD", "MUFU", "UTMALDG", "UBLKCP", "SYNCS", "USETMAXREG", "LDS", "STS", "LDG", "STG", "LDL", "STL",
+KEYS = ["DMMA", "UTCIMMA", "LDTM", "UTCBAR", "DFMA", "DMUL", "DADD", "MUFU", "UTMALDG", "UBLKCP", "SYNCS", "USETMAXREG", "LDS", "STS", "LDG", "STG", "LDL", "STL",
         "ST.E.STRONG.SYS", "LD.E.STRONG.SYS", "BAR", "SHFL"]
 
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
@@ -33,11 +33,11 @@ def demangle(n):
     return subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip().replace("anml::", "")
 
 
-WANT = ["fused_hess_kernel<4, 2, false, 0, true, 32>", "fused_hess_kernel<4, 2, true, 3, true, 32>", "fused_hess_kernel<4, 2, true, 1, true, 32>",
-        "fused_hess_kernel<1, 4, false, 0, true, 64>", "fused_eval_kernel<4, false, 0>", "wide_hessian_kernel", "spline_banded_eval_kernel<3, true, false>",
+WANT = ["fused_hess_i8_kernel", "fused_hess_kernel<4, 2, false, 0, true, 32>", "fused_hess_kernel<4, 2, true, 3, true, 32>", "fused_hess_kernel<4, 2, true, 1, true, 32>",
+        "fused_hess_kernel<1, 4, false, 0, true, 64>", "fused_eval_kernel<4, false, 0>", "wide_hessian_kernel", "spline_banded_bulk_kernel<3, true, false>", "spline_banded_eval_kernel<3, true, false>",
         "spline_design_kernel<3>", "finish_fused_kernel", "banded_finish_kernel", "comm_allreduce_kernel"]
 print("# SASS opcode counts per kernel (static instructions; `cuobjdump -sass` of the shipped library)\n")
-print("DMMA = `mma.sync.m8n8k4.f64` (the FP64 tensor-core instruction of sm_100a); UTMALDG = `cp.async.bulk.tensor` (TMA); "
+print("DMMA = `mma.sync.m8n8k4.f64` (the FP64 tensor-core instruction of sm_100a); UTCIMMA = `tcgen05.mma.kind::i8` (INT8 tensor cores, accumulators in TMEM), LDTM = `tcgen05.ld`, UTCBAR = `tcgen05.commit`; UTMALDG = `cp.async.bulk.tensor` (TMA); "
       "UBLKCP = `cp.async.bulk`; SYNCS = mbarrier operations; USETMAXREG = `setmaxnreg`; LDL / STL = local-memory (spill) traffic.\n")
 hdr = ["kernel", "instr"] + KEYS
 print("| " + " | ".join(hdr) + " |")
