@@ -129,6 +129,7 @@ struct anml_model {
     bool prior_enabled = true;
     bool force_generic = false, no_fast = false, no_specialise = false, banded_registers = false;
     bool force_signed = false;
+    unsigned long long se_version = 0;  // bumped by anml_model_set_obs_se
     bool no_i8 = false;  // option "hess_i8" = 0: keep the Hessian of 64-column logistic / Gaussian models on DMMA
     // INT8-tensor-core Hessian (fused_hess_i8.cuh): column scales of the design they were taken from, flush scratch
     struct I8State {
@@ -137,6 +138,9 @@ struct anml_model {
         long long n = 0;
         unsigned long long version = 0;
         bool usable = false;
+        const double* se = nullptr;           // obs_se vector the bound on sqrt(w) = 1 / se was taken from
+        unsigned long long se_version = 0;
+        double sv_scale = 1.0;                // power of two with sqrt(w) sv_scale <= 1/2
         double* cs = nullptr;                 // [64] scales | [64] reciprocals
         unsigned long long* colmax = nullptr; // [64] bit patterns of the column maxima
         double* scratch = nullptr;            // [sm_count][128][64]
@@ -979,6 +983,7 @@ extern "C" int anml_model_set_obs(anml_model* m, const double* obs, int on_devic
 
 extern "C" int anml_model_set_obs_se(anml_model* m, const double* se, int on_device) {
     if (!m) return fail(ANML_EINVAL, "anml_model_set_obs_se: NULL model");
+    m->se_version++;
     return set_row_vector(m, se, on_device, &m->se, &m->se_owned);
 }
 
@@ -1351,7 +1356,7 @@ static int run_fused_block(anml_model* m, const anml_design* d, FusedArgs a, boo
 
 // ---- Hessian on the INT8 tensor cores (fused_hess_i8.cuh) -------------------------------------------------
 // One-parameter models whose sqrt(w) has a bound known in advance: canonical logistic (w <= 1/4) and the
-// Gaussian identity model with unit obs_se (w = 1).  64 columns, dense row pitch, no per-row weights.
+// Gaussian identity model (w = 1 / obs_se^2 <= 1 / min(obs_se)^2).  64 columns, dense row pitch, no per-row weights.
 static bool i8_eligible(const anml_model* m, const anml_design* d, bool hess) {
     if (!hess || m->no_i8 || m->no_fast || m->no_specialise || m->force_signed || m->force_generic) return false;
     if (m->K != 1 || d->p != 64 || d->ld != 64 || !d->has3d || m->weights) return false;
@@ -1359,7 +1364,7 @@ static bool i8_eligible(const anml_model* m, const anml_design* d, bool hess) {
         if (s[0] == '0') return false;
     const int link = m->par[0].link;
     if (m->family == ANML_FAMILY_BINOMIAL && link == ANML_LINK_EXPIT) return true;
-    if (m->family == ANML_FAMILY_GAUSSIAN && link == ANML_LINK_IDENTITY && !m->se) return true;
+    if (m->family == ANML_FAMILY_GAUSSIAN && link == ANML_LINK_IDENTITY) return true;  // sqrt(w) = 1 / obs_se <= 1 / min(obs_se)
     return false;
 }
 
@@ -1367,7 +1372,7 @@ static bool i8_eligible(const anml_model* m, const anml_design* d, bool hess) {
 // design (and again after the library rewrote it).  A NaN or infinite column keeps the model on the DMMA path.
 static int i8_prepare(anml_model* m, const anml_design* d, cudaStream_t st) {
     anml_model::I8State& s = m->i8;
-    if (s.design == d && s.X == d->X && s.n == d->n && s.version == d->version) return ANML_OK;
+    if (s.design == d && s.X == d->X && s.n == d->n && s.version == d->version && s.se == m->se && s.se_version == m->se_version) return ANML_OK;
     if (!s.cs) CU_TRY(cudaMalloc(&s.cs, 128 * sizeof(double)));
     if (!s.colmax) CU_TRY(cudaMalloc(&s.colmax, 64 * sizeof(unsigned long long)));
     if (!s.scratch) CU_TRY(cudaMalloc(&s.scratch, (size_t)m->sm_count * 4 * 64 * 64 * sizeof(double)));
@@ -1390,7 +1395,26 @@ static int i8_prepare(anml_model* m, const anml_design* d, cudaStream_t st) {
     }
     CU_TRY(cudaMemcpyAsync(s.cs, cs, sizeof(cs), cudaMemcpyHostToDevice, st));
     CU_TRY(cudaStreamSynchronize(st));
-    s.design = d; s.X = d->X; s.n = d->n; s.version = d->version; s.usable = ok;
+    // bound on sqrt(w): 1/2 for the logistic; 1 / min(obs_se) for the Gaussian (1 without obs_se)
+    double sv_max = 0.5;
+    if (m->family == ANML_FAMILY_GAUSSIAN) {
+        sv_max = 1.0;
+        if (m->se) {
+            double lo = 0.0, hi = 0.0;
+            int nan = 0;
+            TRY(anml_vector_minmax(m->device, m->se, m->n, 1, &lo, &hi, &nan));
+            if (nan || !(lo > 0.0) || !std::isfinite(hi)) ok = false;
+            else sv_max = 1.0 / lo;
+        }
+    }
+    s.sv_scale = 1.0;
+    if (ok) {
+        int e = 0;
+        const double f = std::frexp(sv_max, &e);                       // sv_max = f 2^e, f in [1/2, 1)
+        s.sv_scale = std::ldexp(1.0, f == 0.5 ? -e : -(e + 1));        // sv_max sv_scale <= 1/2
+        if (!std::isfinite(s.sv_scale) || s.sv_scale == 0.0 || !std::isfinite(1.0 / (s.sv_scale * s.sv_scale))) ok = false;
+    }
+    s.design = d; s.X = d->X; s.n = d->n; s.version = d->version; s.se = m->se; s.se_version = m->se_version; s.usable = ok;
     m->all_launches += 1;
     return ANML_OK;
 }
@@ -1410,8 +1434,7 @@ static int run_fused_i8(anml_model* m, const anml_design* d, FusedArgs a, const 
     a.status = m->d_status;
     I8Extra x;
     x.cs = m->i8.cs; x.scratch = m->i8.scratch;
-    // sqrt(w) sv_scale <= 1/2: the logistic weight is at most 1/4; the unit-variance Gaussian has sqrt(w) = 1
-    x.sv_scale = (m->family == ANML_FAMILY_BINOMIAL) ? 1.0 : 0.5;
+    x.sv_scale = m->i8.sv_scale;  // sqrt(w) sv_scale <= 1/2 (i8_prepare)
     x.out_scale = 1.0 / (x.sv_scale * x.sv_scale);
     EventPair* ep = next_events(m);
     if (ep) CU_TRY(cudaEventRecord(ep->a, st));
@@ -1897,8 +1920,8 @@ extern "C" int anml_model_eval(anml_model* m, const double* x_host, int want, do
     m->eval_pending = false;
     if (m->h_packed[flag_at] >= 1024.0) {
         m->i8.design = nullptr;  // rescan the column maxima at the next evaluation
-        return fail(ANML_ESTATE, "design values outside the column ranges recorded for the INT8 Hessian path (was a wrapped matrix rewritten in place?); "
-                                 "the ranges are taken again at the next evaluation");
+        return fail(ANML_ESTATE, "design or obs_se values outside the ranges recorded for the INT8 Hessian path (was a borrowed device array rewritten in "
+                                 "place?); the ranges are taken again at the next evaluation");
     }
     if (m->h_packed[flag_at] != 0.0) return fail(ANML_EDOMAIN, "linear predictor outside the domain of a Log/Logit mapping");
     if (want & ANML_WANT_OBJ) *obj = m->h_packed[0];

@@ -404,13 +404,38 @@ def test_i8_hessian_many_epochs_against_dmma():
     assert np.abs(got2[2] - ref2[2]).max() <= 1e-11 * np.abs(ref2[2]).max()
 
 
-def test_i8_not_used_outside_its_domain():
-    # per-row weights, obs_se, Poisson, p != 64: the DMMA kernel
+def test_i8_hessian_gaussian_with_obs_se():
+    # sqrt(w) = 1 / obs_se: the bound comes from min(obs_se), taken when the model is first evaluated
     from anml_b200 import _native as N
 
-    X, obs, se, off, link, x = make_problem("gaussian", 5000, 64, 3, with_se=True)
-    got = gpu_eval("gaussian", X, obs, se, None, link, x)
+    n = 40009
+    X, obs, se, off, link, x = make_problem("gaussian", n, 64, 3, with_se=True)
+    se = se * np.exp2(np.random.default_rng(4).integers(-6, 7, size=n))  # standard errors over four decades
+    design = N.Design(n, 64)
+    design.set_columns(0, X)
+    model = N.NativeModel(n, "gaussian", 1)
+    model.set_param(0, design, N.LINK_CODES["Identity"])
+    model.set_obs(obs)
+    model.set_obs_se(se)
+    got = model.eval(x)
+    assert model.main_kernel().startswith("fused_hess_i8_kernel"), model.main_kernel()
     want = O.model_eval_fused("gaussian", obs, [X], [link], x, obs_se=se)
+    check(got, want)
+    # a new obs_se vector with a smaller minimum: the bound is taken again, not reused
+    se2 = se * 2.0**-9
+    model.set_obs_se(se2)
+    got2 = model.eval(x)
+    assert model.main_kernel().startswith("fused_hess_i8_kernel")
+    check(got2, O.model_eval_fused("gaussian", obs, [X], [link], x, obs_se=se2))
+
+
+def test_i8_not_used_outside_its_domain():
+    # per-row weights, Poisson, p != 64: the DMMA kernel
+    from anml_b200 import _native as N
+
+    X, obs, se, off, link, x = make_problem("poisson", 5000, 64, 3)
+    got = gpu_eval("poisson", X, obs, None, None, link, x)
+    want = O.model_eval_fused("poisson", obs, [X], [link], x)
     check(got, want)
     model, prob, keep = i8_model("binomial", 4000, seed=9)
     model.set_weights(np.linspace(0.5, 1.5, 4000))
