@@ -1,7 +1,8 @@
 """Run-to-run repeatability of every kernel family, as a stand-in for compute-sanitizer racecheck (closed on
 this pool: profiles/r2_sanitizer_note.txt).  Every result is a fixed-order sum, so a data race in the
-helper -> tensor-warp hand-off of fused_hess_kernel (csrc/fused_hess.cuh), in the full/empty barriers of
-wide_hessian_kernel or in the stage ring of spline_banded_bulk_kernel shows up as a run-to-run difference of
+helper -> tensor-warp hand-off of fused_hess_kernel (csrc/fused_hess.cuh), in the TMA / pair-barrier / in-place digit
+write / tcgen05 commit chain of fused_hess_i8_kernel, in the full/empty barriers of wide_hessian_kernel or in the
+stage ring of spline_banded_bulk_kernel shows up as a run-to-run difference of
 some bit: each case is evaluated REPS times at a size that gives every CTA several blocks and must return
 bit-identical records, at alternating coefficient vectors (so a stale buffer from the previous launch is
 caught too)."""
@@ -55,6 +56,16 @@ def logistic_model(n, p, seed, link="Expit", family="binomial"):
 def test_repeatability_fused(n, p):
     model, xs = logistic_model(n, p, seed=n + p)
     o, g, H = repeat_eval(model, xs)
+    assert np.array_equal(H, H.T)
+
+
+def test_repeatability_fused_dmma_at_64_columns():
+    # p = 64 logistic defaults to the INT8-tensor-core Hessian (csrc/fused_hess_i8.cuh, covered above); this is the DMMA
+    # kernel at the same shape
+    model, xs = logistic_model(600_011, 64, seed=8)
+    model.set_option("hess_i8", 0)
+    o, g, H = repeat_eval(model, xs)
+    assert model.main_kernel().startswith("fused_hess_kernel"), model.main_kernel()
     assert np.array_equal(H, H.T)
 
 
