@@ -171,10 +171,17 @@ def test_north_star_logistic_100m_rows_against_torch_fp64():
     for lo in range(0, n, chunk):
         Xc, oc = X[lo:lo + chunk], obs[lo:lo + chunk]
         y = Xc @ xb
-        th = torch.sigmoid(y)
-        obj += (torch.nn.functional.softplus(-y) + (1 - oc) * y).sum()
-        grad += Xc.t() @ (th - oc)
-        hess += (Xc.t() * (th * (1 - th))) @ Xc
+        # the reference's own expressions (smoothmapping.py:119-126 for expit and its derivatives, binomial NLL through
+        # log(theta), log(1 - theta)), not a numerically friendlier restatement
+        z = torch.exp(-y)
+        th = 1.0 / (1.0 + z)
+        d1 = z / (1.0 + z) ** 2
+        d2 = z * (z - 1.0) / (z + 1.0) ** 3
+        obj += -(oc * torch.log(th) + (1 - oc) * torch.log(1 - th)).sum()
+        dl = -oc / th + (1 - oc) / (1 - th)
+        d2l = oc / th**2 + (1 - oc) / (1 - th) ** 2
+        grad += Xc.t() @ (dl * d1)
+        hess += (Xc.t() * (d2l * d1 * d1 + dl * d2)) @ Xc
     obj += 0.5 * (xb**2).sum()
     grad += xb
     hess += torch.eye(p, dtype=torch.float64, device="cuda")
