@@ -22,8 +22,8 @@
 // path to ~1e-14 of its largest entry (tests/test_gpu_fused.py), far inside the 1e-9 of BASELINE.json.  Integer sums
 // do not depend on the order: results are bitwise reproducible.
 //
-// Roles (one persistent CTA per SM, 480 threads, 128 registers):
-//   * 14 helper warps = 7 pairs; a pair owns whole 32-row blocks, each warp 16 rows of them (lanes 16..31 mirror
+// Roles (one persistent CTA per SM, 352 threads, 168 registers):
+//   * 10 helper warps = 5 pairs; a pair owns whole 32-row blocks, each warp 16 rows of them (lanes 16..31 mirror
 //     0..15 while the 16 rows' link / family terms are taken);
 //   * 1 control warp: lane 0 requests blocks by TMA LOOKAHEAD ahead, and as each block's pair reports its digit
 //     planes ready issues the four MMAs and commits them to the buffer's free[] barrier; it closes every epoch.
@@ -44,11 +44,18 @@ struct I8Extra {
 };
 
 struct I8Cfg {
-    static constexpr int PAIRS = 7;                            // helper warp pairs: a pair owns a 32-row block, each warp 16 rows of it
+#ifndef ANML_I8_PAIRS
+#define ANML_I8_PAIRS 5
+#endif
+    static constexpr int PAIRS = ANML_I8_PAIRS;                            // helper warp pairs: a pair owns a 32-row block, each warp 16 rows of it
     static constexpr int NHELP = 2 * PAIRS;
-    static constexpr int THREADS = 32 * (NHELP + 1);           // 480 (128 registers per thread)
+    static constexpr int THREADS = 32 * (NHELP + 1);           // 352: 168 registers per thread, which the helpers need to stay out of local memory
+                                                               // (7 pairs at 128 registers spill and lose 4 %, 6 pairs likewise, 4 pairs are too few: profiles/r2_ab_i8.txt)
     static constexpr int BUF_BYTES = 16384;                    // one block: 4 column groups x 32 rows x 128 B, later its digit planes
-    static constexpr int NBUF = 12;
+#ifndef ANML_I8_NBUF
+#define ANML_I8_NBUF 12
+#endif
+    static constexpr int NBUF = ANML_I8_NBUF;
     static constexpr int LOOKAHEAD = 10;                       // blocks requested from HBM ahead of the MMA issue
     static constexpr int SBO = 1024, LBO = 144, PAIR_STRIDE = 288;
     static constexpr int EPOCH = 4095;                         // blocks between flushes: 2^14 * 32 * 4095 < 2^31 (one product per accumulator and row)
