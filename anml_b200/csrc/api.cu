@@ -1421,8 +1421,8 @@ static int i8_prepare(anml_model* m, const anml_design* d, cudaStream_t st) {
 
 static int run_fused_i8(anml_model* m, const anml_design* d, FusedArgs a, const FinishPlan& plan, double* packed, cudaStream_t st) {
     using C = I8Cfg;
-    static ConfiguredOn configured;
     auto kern = fused_hess_i8_kernel;
+    static ConfiguredOn configured;
     if (!configured.has(d->device)) {
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured.set(d->device);
