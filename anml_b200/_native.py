@@ -67,6 +67,7 @@ SIGNATURES = {
     "anml_model_eval_async": (C.c_int, [C.c_void_p, _c_double_p, C.c_int, C.c_void_p, C.c_void_p]),
     "anml_model_kernel_time": (C.c_int, [C.c_void_p, C.c_int, _c_double_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "anml_model_main_kernel": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "anml_model_last_kernels": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "anml_model_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "anml_comm_handle_bytes": (C.c_int, [C.POINTER(C.c_int)]),
     "anml_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
@@ -491,6 +492,11 @@ class NativeModel:
         buf = C.create_string_buffer(200)
         check(load().anml_model_main_kernel(self.handle, buf, 200))
         return buf.value.decode()
+
+    def last_kernels(self):
+        buf = C.create_string_buffer(1000)
+        check(load().anml_model_last_kernels(self.handle, buf, 1000))
+        return [k for k in buf.value.decode().split(";") if k]
 
     def free(self):
         if getattr(self, "handle", None) is not None and _lib is not None:

@@ -130,6 +130,8 @@ struct anml_model {
     bool force_generic = false, no_fast = false, no_specialise = false, banded_registers = false;
     bool force_signed = false;
     unsigned long long se_version = 0;  // bumped by anml_model_set_obs_se
+    unsigned long long obs_version = 0; // bumped by anml_model_set_obs
+    std::string last_kernels;           // timed kernels of the last evaluation, ';'-separated
     bool no_i8 = false;  // option "hess_i8" = 0: keep the Hessian of 64-column logistic / Gaussian models on DMMA
     // INT8-tensor-core Hessian (fused_hess_i8.cuh): column scales of the design they were taken from, flush scratch
     struct I8State {
@@ -141,6 +143,12 @@ struct anml_model {
         const double* se = nullptr;           // obs_se vector the bound on sqrt(w) = 1 / se was taken from
         unsigned long long se_version = 0;
         double sv_scale = 1.0;                // power of two with sqrt(w) sv_scale <= 1/2
+        double colmax_h[64] = {};             // host copy of the column maxima (bounds on the linear predictors)
+        // mean / variance models (config #4): largest |obs| and |offset_k|, for the per-evaluation bounds on sqrt(w)
+        const double* obs = nullptr;
+        const double* off[2] = {nullptr, nullptr};
+        unsigned long long obs_version = 0;
+        double obs_absmax = 0.0, off_absmax[2] = {0.0, 0.0};
         double* cs = nullptr;                 // [64] scales | [64] reciprocals
         unsigned long long* colmax = nullptr; // [64] bit patterns of the column maxima
         double* scratch = nullptr;            // [sm_count][128][64]
@@ -978,6 +986,7 @@ static int set_row_vector(anml_model* m, const double* src, int on_device, const
 
 extern "C" int anml_model_set_obs(anml_model* m, const double* obs, int on_device) {
     if (!m || !obs) return fail(ANML_EINVAL, "anml_model_set_obs: NULL argument");
+    m->obs_version++;
     return set_row_vector(m, obs, on_device, &m->obs, &m->obs_owned);
 }
 
@@ -1349,6 +1358,7 @@ static int run_fused_block(anml_model* m, const anml_design* d, FusedArgs a, boo
     TRY(rc);
     if (ep) CU_TRY(cudaEventRecord(ep->b, st));
     m->main_kernel = g_kernel;
+    m->last_kernels += (m->last_kernels.empty() ? "" : ";") + m->main_kernel;
     m->main_launches += 1;
     m->all_launches += 1;
     return launch_finish(m, grid, nb16, hess, d->p, plan, packed, st);
@@ -1372,7 +1382,10 @@ static bool i8_eligible(const anml_model* m, const anml_design* d, bool hess) {
 // design (and again after the library rewrote it).  A NaN or infinite column keeps the model on the DMMA path.
 static int i8_prepare(anml_model* m, const anml_design* d, cudaStream_t st) {
     anml_model::I8State& s = m->i8;
-    if (s.design == d && s.X == d->X && s.n == d->n && s.version == d->version && s.se == m->se && s.se_version == m->se_version) return ANML_OK;
+    const bool meanvar = m->family == ANML_FAMILY_GAUSSIAN_MEANVAR;
+    if (s.design == d && s.X == d->X && s.n == d->n && s.version == d->version && s.se == m->se && s.se_version == m->se_version &&
+        (!meanvar || (s.obs == m->obs && s.obs_version == m->obs_version && s.off[0] == m->par[0].offset && s.off[1] == m->par[1].offset)))
+        return ANML_OK;
     if (!s.cs) CU_TRY(cudaMalloc(&s.cs, 128 * sizeof(double)));
     if (!s.colmax) CU_TRY(cudaMalloc(&s.colmax, 64 * sizeof(unsigned long long)));
     if (!s.scratch) CU_TRY(cudaMalloc(&s.scratch, (size_t)m->sm_count * 4 * 64 * 64 * sizeof(double)));
@@ -1392,6 +1405,22 @@ static int i8_prepare(anml_model* m, const anml_design* d, cudaStream_t st) {
         if (ok && mx > 0.0) (void)std::frexp(mx, &e);  // mx = f 2^e, f in [1/2, 1)
         cs[j] = (ok && mx > 0.0) ? std::ldexp(1.0, -(e + 1)) : 1.0;
         cs[64 + j] = 1.0 / cs[j];
+        s.colmax_h[j] = mx;
+    }
+    if (meanvar && ok) {
+        auto absmax = [&](const double* v, double* out) -> int {
+            *out = 0.0;
+            if (!v) return ANML_OK;
+            double lo = 0.0, hi = 0.0;
+            int nan = 0;
+            TRY(anml_vector_minmax(m->device, v, m->n, 1, &lo, &hi, &nan));
+            if (nan || !std::isfinite(lo) || !std::isfinite(hi)) ok = false;
+            *out = std::fmax(std::fabs(lo), std::fabs(hi));
+            return ANML_OK;
+        };
+        TRY(absmax(m->obs, &s.obs_absmax));
+        TRY(absmax(m->par[0].offset, &s.off_absmax[0]));
+        TRY(absmax(m->par[1].offset, &s.off_absmax[1]));
     }
     CU_TRY(cudaMemcpyAsync(s.cs, cs, sizeof(cs), cudaMemcpyHostToDevice, st));
     CU_TRY(cudaStreamSynchronize(st));
@@ -1415,18 +1444,39 @@ static int i8_prepare(anml_model* m, const anml_design* d, cudaStream_t st) {
         if (!std::isfinite(s.sv_scale) || s.sv_scale == 0.0 || !std::isfinite(1.0 / (s.sv_scale * s.sv_scale))) ok = false;
     }
     s.design = d; s.X = d->X; s.n = d->n; s.version = d->version; s.se = m->se; s.se_version = m->se_version; s.usable = ok;
+    s.obs = m->obs; s.obs_version = m->obs_version; s.off[0] = m->par[0].offset; s.off[1] = m->K > 1 ? m->par[1].offset : nullptr;
     m->all_launches += 1;
     return ANML_OK;
 }
 
-static int run_fused_i8(anml_model* m, const anml_design* d, FusedArgs a, const FinishPlan& plan, double* packed, cudaStream_t st) {
+constexpr bool I8_DUAL_DEFAULT = false;
+
+// power of two s with sv_max * s <= 1/2
+static double i8_scale_for(double sv_max) {
+    int e = 0;
+    const double f = std::frexp(sv_max, &e);  // sv_max = f 2^e, f in [1/2, 1)
+    return std::ldexp(1.0, f == 0.5 ? -e : -(e + 1));
+}
+
+template <int MODE>
+static int launch_i8_t(const anml_design* d, const FusedArgs& a, const I8Extra& x, int grid, cudaStream_t st) {
     using C = I8Cfg;
-    auto kern = fused_hess_i8_kernel;
     static ConfiguredOn configured;
+    auto kern = fused_hess_i8_kernel<MODE>;
     if (!configured.has(d->device)) {
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured.set(d->device);
     }
+    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(d->tmap3d, a, x);
+    CU_TRY(cudaGetLastError());
+    if (MODE == 0) snprintf(g_kernel, sizeof(g_kernel), "fused_hess_i8_kernel");
+    else snprintf(g_kernel, sizeof(g_kernel), "fused_hess_i8_kernel<%d>", MODE);
+    return ANML_OK;
+}
+
+// mode 0: one-parameter model; 3: both predictors of a mean / variance model + block (0,0); 1: term-fed block
+static int run_fused_i8(anml_model* m, const anml_design* d, FusedArgs a, int mode, double sv_scale, const FinishPlan& plan, double* packed,
+                        cudaStream_t st) {
     const long long nblk = (d->n + 31) / 32;
     int grid = nblk < m->sm_count ? (int)nblk : m->sm_count;
     if (grid < 1) grid = 1;
@@ -1434,18 +1484,49 @@ static int run_fused_i8(anml_model* m, const anml_design* d, FusedArgs a, const 
     a.status = m->d_status;
     I8Extra x;
     x.cs = m->i8.cs; x.scratch = m->i8.scratch;
-    x.sv_scale = m->i8.sv_scale;  // sqrt(w) sv_scale <= 1/2 (i8_prepare)
+    x.sv_scale = sv_scale;  // sqrt(w) sv_scale <= 1/2
     x.out_scale = 1.0 / (x.sv_scale * x.sv_scale);
     EventPair* ep = next_events(m);
     if (ep) CU_TRY(cudaEventRecord(ep->a, st));
-    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(d->tmap3d, a, x);
-    CU_TRY(cudaGetLastError());
+    int rc = ANML_OK;
+    if (mode == 3) rc = launch_i8_t<3>(d, a, x, grid, st);
+    else if (mode == 1) rc = launch_i8_t<1>(d, a, x, grid, st);
+    else rc = launch_i8_t<0>(d, a, x, grid, st);
+    TRY(rc);
     if (ep) CU_TRY(cudaEventRecord(ep->b, st));
-    snprintf(g_kernel, sizeof(g_kernel), "fused_hess_i8_kernel");
     m->main_kernel = g_kernel;
+    m->last_kernels += (m->last_kernels.empty() ? "" : ";") + m->main_kernel;
     m->main_launches += 1;
     m->all_launches += 1;
     return launch_finish(m, grid, 4, true, d->p, plan, packed, st);
+}
+
+// Mean (identity) / variance (exp) model over one 64-column design (BASELINE config #4): H00 = U^T U with U = e^{-y1/2} X
+// and H11 = V^T V with V = sqrt(w11) X = |res| e^{-y1/2} / sqrt(2) X go to the INT8 tensor cores when sqrt(w) can be
+// bounded tightly enough in advance: |y_k| <= max|offset_k| + sum_j max_i|x_ij| |beta_kj|, |res| <= max|obs| + |y0| bound.
+// A bound costs one bit of the 48 per factor of two it overshoots; beyond 2^10 (block 00) / 2^12 (block 11) the DMMA kernels run.
+static bool i8_dual_bounds(const anml_model* m, const anml_design* d, double* scale_u, double* scale_v) {
+    if (m->no_i8 || m->no_fast || m->no_specialise || m->force_signed || m->force_generic || m->weights) return false;
+    if (!I8_DUAL_DEFAULT) {  // not yet validated on hardware in this build: opt-in
+        const char* s = getenv("ANML_B200_HESS_I8_DUAL");
+        if (!s || s[0] != '1') return false;
+    }
+    if (d->p != 64 || d->ld != 64 || !d->has3d) return false;
+    if (m->family != ANML_FAMILY_GAUSSIAN_MEANVAR || m->par[0].link != ANML_LINK_IDENTITY || m->par[1].link != ANML_LINK_EXP) return false;
+    if (const char* s = getenv("ANML_B200_HESS_I8"))
+        if (s[0] == '0') return false;
+    if (!m->i8.usable) return false;
+    double s0 = m->i8.off_absmax[0], s1 = m->i8.off_absmax[1];
+    for (int j = 0; j < 64; ++j) {
+        s0 += m->i8.colmax_h[j] * std::fabs(m->h_beta[m->par[0].off + j]);
+        s1 += m->i8.colmax_h[j] * std::fabs(m->h_beta[m->par[1].off + j]);
+    }
+    const double hmax = std::exp(0.5 * s1);
+    const double sv_u = hmax, sv_v = (m->i8.obs_absmax + s0) * hmax * 0.70710678118654757;
+    if (!(sv_u <= 1024.0) || !(sv_v <= 4096.0) || !(sv_v > 0.0)) return false;
+    *scale_u = i8_scale_for(sv_u);
+    *scale_v = i8_scale_for(sv_v);
+    return true;
 }
 
 // Gaussian prior terms as a separate launch: only the paths whose epilogue is not the fused one
@@ -1522,6 +1603,7 @@ static int run_wide_hessian(anml_model* m, const anml_design* da, const anml_des
     CU_TRY(cudaGetLastError());
     if (ep) CU_TRY(cudaEventRecord(ep->b, st));
     m->main_kernel = "wide_hessian_kernel";
+    m->last_kernels += (m->last_kernels.empty() ? "" : ";") + m->main_kernel;
     const long long total = (long long)npairs * WIDE_TILE_ELEMS;
     wide_reduce_kernel<<<grid_for(total, 256, m->sm_count, 8), 256, 0, st>>>(m->d_wide, (int)S, npairs, nbb, symmetric ? 1 : 0, da->p, db->p,
                                                                             packed + 1 + m->P, m->P, row_off, col_off);
@@ -1611,6 +1693,7 @@ static int eval_banded(anml_model* m, int want, double* packed, cudaStream_t st)
     snprintf(g_kernel, sizeof(g_kernel), "%s<%d, %d, %d>", bulk ? "spline_banded_bulk_kernel" : "spline_banded_eval_kernel", b.degree, hess ? 1 : 0,
              extras ? 1 : 0);
     m->main_kernel = g_kernel;
+    m->last_kernels += (m->last_kernels.empty() ? "" : ";") + m->main_kernel;
     banded_reduce_kernel<<<(b.rec + 31) / 32, dim3(32, 32), 0, st>>>(b.partials, b.grid, b.rec, b.reduced);
     CU_TRY(cudaGetLastError());
     BandedFinishArgs f;
@@ -1746,6 +1829,7 @@ static int eval_on_stream(anml_model* m, const double* x_host, int want, double*
     // d_status is zero here: zeroed at allocation, and every evaluation's last launch re-arms it
 
     const anml_design* d0 = m->par[0].design;
+    m->last_kernels.clear();
     if (banded) {
         TRY(eval_banded(m, want, packed, st));
     } else if (m->K == 1 && d0->p <= 64 && !m->force_generic) {
@@ -1760,7 +1844,7 @@ static int eval_on_stream(anml_model* m, const double* x_host, int want, double*
             TRY(i8_prepare(m, d0, st));
             i8 = m->i8.usable;
         }
-        if (i8) TRY(run_fused_i8(m, d0, a, plan, packed, st));
+        if (i8) TRY(run_fused_i8(m, d0, a, 0, m->i8.sv_scale, plan, packed, st));
         else TRY(run_fused_block(m, d0, a, hess, 0, plan, packed, true, st));
     } else {
         TRY(eval_general(m, want, packed, st));
@@ -1792,6 +1876,37 @@ static int eval_general(anml_model* m, int want, double* packed, cudaStream_t st
     if (dual) {
         const anml_design* d = m->par[0].design;
         const int off0 = m->par[0].off, off1 = m->par[1].off;
+        double scale_u = 1.0, scale_v = 1.0;
+        bool i8 = false;
+        if (hess && !m->no_specialise && !m->no_i8 && m->family == ANML_FAMILY_GAUSSIAN_MEANVAR && d->p == 64 && d->ld == 64 && d->has3d) {
+            TRY(i8_prepare(m, d, st));
+            i8 = i8_dual_bounds(m, d, &scale_u, &scale_v);
+        }
+        if (i8) {
+            // blocks (0,0) and (1,1) on the INT8 tensor cores, the signed cross block (0,1) on DMMA
+            FusedArgs a;
+            memset(&a, 0, sizeof(a));
+            a.n = m->n; a.p = d->p; a.link = m->par[0].link; a.link1 = m->par[1].link; a.family = m->family; a.fast = 1;
+            a.beta = m->d_beta + m->par[0].pad_off; a.beta1 = m->d_beta + m->par[1].pad_off;
+            a.obs = m->obs; a.offset = m->par[0].offset; a.offset1 = m->par[1].offset;
+            a.out_r1 = m->vec[3]; a.out_w01 = m->vec[5]; a.out_w11 = m->vec[6];  // vec[6] receives sqrt(w11) here
+            FinishPlan p0;
+            p0.row_off = off0; p0.col_off = off0; p0.prior_k = 0; p0.prior_obj = true;
+            TRY(run_fused_i8(m, d, a, 3, scale_u, p0, packed, st));
+            FusedArgs b;
+            memset(&b, 0, sizeof(b));
+            b.n = m->n; b.p = d->p; b.rvec = m->vec[3]; b.wvec = m->vec[6];
+            FinishPlan p1;
+            p1.row_off = off1; p1.col_off = off1; p1.prior_k = 1; p1.obj_mode = 0;
+            TRY(run_fused_i8(m, d, b, 1, scale_v, p1, packed, st));
+            FusedArgs c;
+            memset(&c, 0, sizeof(c));
+            c.n = m->n; c.p = d->p; c.rvec = nullptr; c.wvec = m->vec[5];
+            FinishPlan px;
+            px.row_off = off0; px.col_off = off1; px.write_grad = false; px.obj_mode = 0; px.write_flag = true;
+            TRY(run_fused_block(m, d, c, true, 1, px, packed, true, st));
+            return ANML_OK;
+        }
         if (hess && !m->no_specialise) {
             FusedArgs a;
             memset(&a, 0, sizeof(a));
@@ -1927,6 +2042,12 @@ extern "C" int anml_model_eval(anml_model* m, const double* x_host, int want, do
     if (want & ANML_WANT_OBJ) *obj = m->h_packed[0];
     if (want & ANML_WANT_GRAD) memcpy(grad, m->h_packed + 1, P * sizeof(double));
     if (want & ANML_WANT_HESS) memcpy(hess, m->h_packed + 1 + P, P * P * sizeof(double));
+    return ANML_OK;
+}
+
+extern "C" int anml_model_last_kernels(const anml_model* m, char* out, int out_len) {
+    if (!m || !out || out_len <= 0) return fail(ANML_EINVAL, "anml_model_last_kernels: bad arguments");
+    snprintf(out, (size_t)out_len, "%s", m->last_kernels.c_str());
     return ANML_OK;
 }
 

@@ -64,7 +64,7 @@ struct I8Cfg {
     static constexpr int TR_BYTES = 4 * 36 * 8;                // per helper: transpose scratch
     static constexpr int HT_BYTES = 256;                       // per helper: r and sqrt(w) of its 16 rows
     static constexpr int HREC_BYTES = (NB8 + 1) * 256;         // per helper: gradient / objective record at the end (in the idle ring)
-    static constexpr int SMEM_BYTES = 1024 + NBUF * BUF_BYTES + 512 /*barriers, TMEM slot*/ + 2 * 64 * 8 + NHELP * (TR_BYTES + HT_BYTES);
+    static constexpr int SMEM_BYTES = 1024 + NBUF * BUF_BYTES + 512 /*barriers, TMEM slot*/ + 3 * 64 * 8 /*beta, column scales, beta1*/ + NHELP * (TR_BYTES + HT_BYTES);
     static_assert(NHELP * HREC_BYTES <= NBUF * BUF_BYTES, "the helper records reuse the ring");
 };
 
@@ -110,6 +110,12 @@ constexpr double I8_MAGIC = 16.0 + (double)0x808080808080ull / 281474976710656.0
 //      (M = N = 128) form pair(pp) x pair(pp') for pp + pp' <= 2 into TMEM block pp + pp' (128 columns), where entry
 //      (m, n) carries weight 2^-8(2 (pp + pp') + 2 + x_m + x_n);
 //   4. the MMAs' commit frees the buffer for the next TMA.
+// MODE 0: row terms of a one-parameter model taken here (binomial/expit, gaussian/identity);
+// MODE 3: two parameters over this one design, mean identity / variance exp (BASELINE config #4): both linear predictors,
+//         the row terms of the pair, objective, g0 and H00 = U^T U with U = sqrt(w00) X = e^{-y1/2} X; writes r1, w01 and
+//         sqrt(w11) to a.out_r1 / out_w01 / out_w11 for the launches that follow;
+// MODE 1: term-fed block: r from a.rvec (nullptr: no gradient), sqrt(w) >= 0 from a.wvec; no y pass, no row terms.
+template <int MODE>
 __global__ void __launch_bounds__(I8Cfg::THREADS, 1) fused_hess_i8_kernel(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const I8Extra x) {
     using C = I8Cfg;
     constexpr int NBUF = C::NBUF, NB8 = C::NB8, NT = C::NT, NHELP = C::NHELP;
@@ -123,7 +129,8 @@ __global__ void __launch_bounds__(I8Cfg::THREADS, 1) fused_hess_i8_kernel(const 
     const uint32_t slot_u32 = done_u32 + 8;                        // TMEM base address
     const uint32_t beta_u32 = full_u32 + 512;
     const uint32_t cs_u32 = beta_u32 + 64 * 8;
-    const uint32_t tr_base = cs_u32 + 64 * 8;
+    const uint32_t beta1_u32 = cs_u32 + 64 * 8;
+    const uint32_t tr_base = beta1_u32 + 64 * 8;
     const uint32_t hterm_base = tr_base + NHELP * C::TR_BYTES;
     const uint32_t hrec_base = smem_base;  // after the last epoch the ring is idle
     static_assert((3 * NBUF + 1) * 8 + 16 <= 512, "barrier area");
@@ -142,7 +149,8 @@ __global__ void __launch_bounds__(I8Cfg::THREADS, 1) fused_hess_i8_kernel(const 
         mbar_fence_init();
     }
     if (threadIdx.x < 64) {
-        sts64(beta_u32 + threadIdx.x * 8, a.beta[threadIdx.x]);
+        sts64(beta_u32 + threadIdx.x * 8, MODE == 1 ? 0.0 : a.beta[threadIdx.x]);
+        sts64(beta1_u32 + threadIdx.x * 8, MODE == 3 ? a.beta1[threadIdx.x] : 0.0);
         sts64(cs_u32 + threadIdx.x * 8, x.cs[threadIdx.x] * x.sv_scale);  // the global factor of sqrt(w) rides on the column scale
     }
     if (warp == NHELP) {
@@ -195,46 +203,77 @@ __global__ void __launch_bounds__(I8Cfg::THREADS, 1) fused_hess_i8_kernel(const 
                 const uint32_t bp = smem_base + buf * C::BUF_BYTES;
                 const long long row = row0 + my_row;
                 const bool valid = row < a.n;
-                double off = 0.0, ob = 0.0, se = 1.0;
-                if (valid) {
-                    if (a.offset) off = a.offset[row];
-                    ob = a.obs[row];
-                    if (a.se) se = a.se[row];
-                }
-                mbar_wait(full_u32 + buf * 8, (uint32_t)((q / NBUF) & 1));
-                // ---- pass 1: linear predictor of this warp's 16 rows
-                double part[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const double2 b = lds128(beta_u32 + (16 * j + 2 * g) * 8);
-#pragma unroll
-                    for (int s = 0; s < 4; ++s) {
-                        const double2 v = lds128(bp + j * 4096 + rd_off[s]);
-                        part[s] = fma(v.y, b.y, fma(v.x, b.x, part[s]));
-                    }
-                }
-                // lane (g,t) stores part[s] at [s][g][t]; the lane at position 4s' + t' adds the 8 entries [s'][*][t']
-#pragma unroll
-                for (int s = 0; s < 4; ++s) sts64(tr_u32 + (s * 36 + lane) * 8, part[s]);
-                __syncwarp();
-                double y;
-                {
-                    const uint32_t base = tr_u32 + ((rl >> 2) * 36 + (rl & 3)) * 8;
-                    const double q0 = lds64(base), q1 = lds64(base + 32), q2 = lds64(base + 64), q3 = lds64(base + 96);
-                    const double q4 = lds64(base + 128), q5 = lds64(base + 160), q6 = lds64(base + 192), q7 = lds64(base + 224);
-                    y = ((q0 + q1) + (q2 + q3)) + ((q4 + q5) + (q6 + q7));
-                }
                 double rr = 0.0, sc = 0.0;
-                if (valid) {
-                    const RowTerms1 rt = row_terms1<true, true>(a.family, a.link, true, y + off, ob, se);
-                    bad_domain |= !rt.ok;
-                    if (lane < 16) {
-                        objacc += rt.l;
-                        logprod.mul(rt.ls);
+                if (MODE == 1) {
+                    // ---- term-fed: r and sqrt(w) of the row come from the vectors of an earlier launch
+                    if (valid) {
+                        if (a.rvec) rr = a.rvec[row];
+                        sc = a.wvec[row];
+                        if (!(sc <= sv_max)) bad_range = 0xffff0000u;
                     }
-                    rr = rt.r;
-                    sc = rt.sw;
-                    if (!(sc <= sv_max)) bad_range = 0xffff0000u;  // outside the digit range: flagged, the host reports it
+                    mbar_wait(full_u32 + buf * 8, (uint32_t)((q / NBUF) & 1));
+                } else {
+                    double off = 0.0, off1 = 0.0, ob = 0.0, se = 1.0;
+                    if (valid) {
+                        if (a.offset) off = a.offset[row];
+                        ob = a.obs[row];
+                        if (MODE == 0 && a.se) se = a.se[row];
+                        if (MODE == 3 && a.offset1) off1 = a.offset1[row];
+                    }
+                    mbar_wait(full_u32 + buf * 8, (uint32_t)((q / NBUF) & 1));
+                    // ---- pass 1: linear predictor(s) of this warp's 16 rows
+                    double part[4] = {0.0, 0.0, 0.0, 0.0}, part1[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double2 b = lds128(beta_u32 + (16 * j + 2 * g) * 8);
+                        const double2 b1 = MODE == 3 ? lds128(beta1_u32 + (16 * j + 2 * g) * 8) : make_double2(0.0, 0.0);
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) {
+                            const double2 v = lds128(bp + j * 4096 + rd_off[s]);
+                            part[s] = fma(v.y, b.y, fma(v.x, b.x, part[s]));
+                            if (MODE == 3) part1[s] = fma(v.y, b1.y, fma(v.x, b1.x, part1[s]));
+                        }
+                    }
+                    // lane (g,t) stores part[s] at [s][g][t]; the lane at position 4s' + t' adds the 8 entries [s'][*][t']
+                    auto transpose_sum = [&](const double (&pt)[4]) {
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) sts64(tr_u32 + (s * 36 + lane) * 8, pt[s]);
+                        __syncwarp();
+                        const uint32_t base = tr_u32 + ((rl >> 2) * 36 + (rl & 3)) * 8;
+                        const double q0 = lds64(base), q1 = lds64(base + 32), q2 = lds64(base + 64), q3 = lds64(base + 96);
+                        const double q4 = lds64(base + 128), q5 = lds64(base + 160), q6 = lds64(base + 192), q7 = lds64(base + 224);
+                        __syncwarp();
+                        return ((q0 + q1) + (q2 + q3)) + ((q4 + q5) + (q6 + q7));
+                    };
+                    const double y = transpose_sum(part);
+                    if (MODE == 0) {
+                        if (valid) {
+                            const RowTerms1 rt = row_terms1<true, true>(a.family, a.link, true, y + off, ob, se);
+                            bad_domain |= !rt.ok;
+                            if (lane < 16) {
+                                objacc += rt.l;
+                                logprod.mul(rt.ls);
+                            }
+                            rr = rt.r;
+                            sc = rt.sw;
+                            if (!(sc <= sv_max)) bad_range = 0xffff0000u;  // outside the digit range: flagged, the host reports it
+                        }
+                    } else {
+                        const double y1 = transpose_sum(part1);
+                        if (valid) {
+                            const RowTerms2 rt = row_terms2(a.link, a.link1, y + off, y1 + off1, ob, true);
+                            bad_domain |= !rt.ok;
+                            if (lane < 16) {
+                                objacc += rt.l;
+                                a.out_r1[row] = rt.r1;
+                                a.out_w01[row] = rt.w01;
+                                a.out_w11[row] = sqrt(rt.w11);  // sqrt(w11) = |res| e^{-y1/2} / sqrt(2): what the MODE 1 launch of block (1,1) reads
+                            }
+                            rr = rt.r0;
+                            sc = rt.sw00;
+                            if (!(sc >= 0.0 && sc <= sv_max) || !(rt.w11 >= 0.0)) bad_range = 0xffff0000u;
+                        }
+                    }
                 }
                 if (lane < 16) {
                     sts64(ht_u32 + lane * 8, rr);

@@ -689,6 +689,7 @@ def run_gpu(args, cfg):
     ms_total = e0.elapsed_time(e1)
     k_ms, k_launches, all_launches = model.native.kernel_time(reset=True)
     main_kernel = model.native.main_kernel()
+    step_kernels = model.native.last_kernels()  # the timed kernels of one evaluation, in launch order
     ms_step, kernel_ms = max_over_ranks([ms_total / steps, k_ms / steps])
     launches_per_step = k_launches / steps
 
@@ -817,16 +818,15 @@ def run_gpu(args, cfg):
                                                  "SYRK convention n*p*(p+1); peak = cuBLAS DGEMM 4096^3 measured in this run"}
         else:
             achieved = flops / (kernel_ms * 1e-3) / 1e12 if kernel_ms > 0 else 0.0
-            if kind == "meanvar":
-                names = [f"fused_hess_kernel<4, 2, 1, 3, 1, 32>", "fused_hess_kernel<4, 2, 1, 1, 1, 32>", "fused_hess_kernel<4, 2, 1, 1, 1, 32>"] if p == 64 else [main_kernel]
-            else:
-                names = [main_kernel]
+            names = step_kernels if kind == "meanvar" else [main_kernel]
             traffic_row, traffic_src = ncu_traffic(names)
-            roofline = {"kernel": main_kernel if kind != "meanvar" else "fused_hess_kernel: MODE 3 (both predictors, H00) + 2 x MODE 1 (H11, H01)",
+            roofline = {"kernel": main_kernel if kind != "meanvar" else " + ".join(step_kernels),
                         "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                         "traffic": None if traffic_row is None else traffic_row * n, "kernel_ms": kernel_ms, "launches_per_step": launches_per_step,
                         "flops_per_launch": flops / max(launches_per_step, 1), "flops_per_step": flops,
-                        "algorithmic": f"SYRK convention n*p*(p+1) per weighted block, {n_blocks} block(s)",
+                        "algorithmic": f"SYRK convention n*p*(p+1) per weighted block, {n_blocks} block(s)"
+                                       + ("; blocks (0,0) and (1,1) on the INT8 tensor cores (exact digit planes, csrc/fused_hess_i8.cuh), the signed "
+                                          "cross block on DMMA: FP64-equivalent rate" if any(k.startswith("fused_hess_i8") for k in step_kernels) else ""),
                         "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (FP64 is absent from MEASURED_PEAKS.json)",
                         "peak_dmma_microbench": dmma_peak, "frac_of_dmma_microbench": achieved / dmma_peak,
                         "traffic_source": traffic_src}

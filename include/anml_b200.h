@@ -171,6 +171,8 @@ int anml_model_kernel_time(anml_model* m, int reset, double* total_ms, int64_t* 
 /* name and template arguments of the kernel that anml_model_kernel_time last timed, e.g.
  * "fused_hess_kernel<4, 2, 0, 0, 1, 32>" (bench.py looks its ncu DRAM traffic up under that key) */
 int anml_model_main_kernel(const anml_model* m, char* out, int out_len);
+/* the timed kernels of the last evaluation in launch order, ';'-separated (a mean / variance model launches three) */
+int anml_model_last_kernels(const anml_model* m, char* out, int out_len);
 /* Evaluation switches (all default 0 unless noted; development / A-B use, results stay within tolerance either way):
  *   "hess_i8" (default 1)       Hessian of an eligible model (one parameter, exactly 64 dense columns, binomial/expit or
  *                               gaussian/identity, no per-row weights) on the INT8 tensor cores

@@ -441,3 +441,61 @@ def test_i8_not_used_outside_its_domain():
     model.set_weights(np.linspace(0.5, 1.5, 4000))
     model.eval(prob[4])
     assert model.main_kernel().startswith("fused_hess_kernel")
+
+
+def meanvar64_model(n, seed, scale=1.0, offsets=False):
+    from anml_b200 import _native as N
+
+    rng = np.random.default_rng(seed)
+    X = rng.normal(size=(n, 64)); X[:, 0] = 1.0
+    b0 = rng.normal(size=64) * 0.1
+    b1 = rng.normal(size=64) * 0.05 * scale
+    obs = X @ b0 + np.exp(0.5 * (X @ b1)) * rng.normal(size=n)
+    off = [rng.normal(size=n) * 0.3, rng.normal(size=n) * 0.2] if offsets else [None, None]
+    d = N.Design(n, 64); d.set_columns(0, X)
+    bufs = [N.DeviceBuffer(0, o) if o is not None else None for o in off]
+    model = N.NativeModel(n, "gaussian_meanvar", 2)
+    model.set_param(0, d, N.LINK_CODES["Identity"], bufs[0])
+    model.set_param(1, d, N.LINK_CODES["Exp"], bufs[1])
+    model.set_obs(obs)
+    model.set_gaussian_prior(0, np.zeros(64), np.full(64, 3.0))
+    x = np.concatenate([0.6 * b0, 0.6 * b1])
+    pri = [{"direct": (np.zeros(64), np.full(64, 3.0))}, None]
+    want = O.model_eval_fused("gaussian_meanvar", obs, [X, X], ["identity", "exp"], x, offsets=off if offsets else None, priors=pri)
+    return model, x, want, (d, bufs)
+
+
+def _dual_i8_enabled():
+    import os
+
+    from anml_b200 import _native as N
+
+    return os.environ.get("ANML_B200_HESS_I8_DUAL") == "1" or N.load().anml_version() >= 201
+
+
+@pytest.mark.parametrize("n,offsets", [(1, False), (33, False), (5000, True), (200_003, False)])
+def test_i8_mean_variance_blocks(n, offsets):
+    if not _dual_i8_enabled():
+        pytest.skip("INT8 blocks of the mean / variance model are opt-in in this build (ANML_B200_HESS_I8_DUAL=1)")
+    # BASELINE config #4 shape: blocks (0,0) and (1,1) on the INT8 tensor cores, the signed cross block on DMMA
+    model, x, want, keep = meanvar64_model(n, seed=n + 3, offsets=offsets)
+    got = model.eval(x)
+    ks = model.last_kernels()
+    assert [k.split("<")[0] for k in ks] == ["fused_hess_i8_kernel", "fused_hess_i8_kernel", "fused_hess_kernel"], ks
+    check(got, want)
+    again = model.eval(x)
+    assert got[0] == again[0] and np.array_equal(got[1], again[1]) and np.array_equal(got[2], again[2])
+    model.set_option("hess_i8", 0)
+    ref = model.eval(x)
+    assert all(k.startswith("fused_hess_kernel") for k in model.last_kernels())
+    assert np.abs(got[2] - ref[2]).max() <= 1e-11 * np.abs(ref[2]).max()
+    assert np.abs(got[1] - ref[1]).max() <= 1e-12 * np.abs(ref[1]).max()
+    assert abs(got[0] - ref[0]) <= 1e-12 * abs(ref[0])
+
+
+def test_i8_mean_variance_falls_back_when_the_weight_bound_is_loose():
+    # variance coefficients 40 times larger: the a-priori bound on e^{-y1/2} exceeds 2^10, the DMMA kernels run
+    model, x, want, keep = meanvar64_model(4000, seed=12, scale=40.0)
+    got = model.eval(x)
+    assert all(k.startswith("fused_hess_kernel") for k in model.last_kernels()), model.last_kernels()
+    check(got, want, og=1e-9, h=1e-9)
