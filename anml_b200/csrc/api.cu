@@ -130,7 +130,6 @@ struct anml_model {
     bool force_generic = false, no_fast = false, no_specialise = false, banded_registers = false;
     bool force_signed = false;
     unsigned long long se_version = 0;  // bumped by anml_model_set_obs_se
-    unsigned long long obs_version = 0; // bumped by anml_model_set_obs
     std::string last_kernels;           // timed kernels of the last evaluation, ';'-separated
     bool no_i8 = false;  // option "hess_i8" = 0: keep the Hessian of 64-column logistic / Gaussian models on DMMA
     // INT8-tensor-core Hessian (fused_hess_i8.cuh): column scales of the design they were taken from, flush scratch
@@ -143,14 +142,9 @@ struct anml_model {
         const double* se = nullptr;           // obs_se vector the bound on sqrt(w) = 1 / se was taken from
         unsigned long long se_version = 0;
         double sv_scale = 1.0;                // power of two with sqrt(w) sv_scale <= 1/2
-        double colmax_h[64] = {};             // host copy of the column maxima (bounds on the linear predictors)
-        // mean / variance models (config #4): largest |obs| and |offset_k|, for the per-evaluation bounds on sqrt(w)
-        const double* obs = nullptr;
-        const double* off[2] = {nullptr, nullptr};
-        unsigned long long obs_version = 0;
-        double obs_absmax = 0.0, off_absmax[2] = {0.0, 0.0};
+
         double* cs = nullptr;                 // [64] scales | [64] reciprocals
-        unsigned long long* colmax = nullptr; // [64] bit patterns of the column maxima
+        unsigned long long* colmax = nullptr; // [64] bit patterns of the column maxima; [64]: max of a weight vector (wmax_kernel)
         double* scratch = nullptr;            // [sm_count][128][64]
     } i8;
     cudaStream_t stream = nullptr;
@@ -986,7 +980,6 @@ static int set_row_vector(anml_model* m, const double* src, int on_device, const
 
 extern "C" int anml_model_set_obs(anml_model* m, const double* obs, int on_device) {
     if (!m || !obs) return fail(ANML_EINVAL, "anml_model_set_obs: NULL argument");
-    m->obs_version++;
     return set_row_vector(m, obs, on_device, &m->obs, &m->obs_owned);
 }
 
@@ -1378,16 +1371,20 @@ static bool i8_eligible(const anml_model* m, const anml_design* d, bool hess) {
     return false;
 }
 
+// power of two s with sv_max * s <= 1/2
+static double i8_scale_for(double sv_max) {
+    int e = 0;
+    const double f = std::frexp(sv_max, &e);  // sv_max = f 2^e, f in [1/2, 1)
+    return std::ldexp(1.0, f == 0.5 ? -e : -(e + 1));
+}
+
 // column scales cs_j = 2^-(e_j + 1), 2^(e_j - 1) <= max_i |x_ij| < 2^(e_j): |x cs| < 1/2.  One pass over X, once per
 // design (and again after the library rewrote it).  A NaN or infinite column keeps the model on the DMMA path.
 static int i8_prepare(anml_model* m, const anml_design* d, cudaStream_t st) {
     anml_model::I8State& s = m->i8;
-    const bool meanvar = m->family == ANML_FAMILY_GAUSSIAN_MEANVAR;
-    if (s.design == d && s.X == d->X && s.n == d->n && s.version == d->version && s.se == m->se && s.se_version == m->se_version &&
-        (!meanvar || (s.obs == m->obs && s.obs_version == m->obs_version && s.off[0] == m->par[0].offset && s.off[1] == m->par[1].offset)))
-        return ANML_OK;
+    if (s.design == d && s.X == d->X && s.n == d->n && s.version == d->version && s.se == m->se && s.se_version == m->se_version) return ANML_OK;
     if (!s.cs) CU_TRY(cudaMalloc(&s.cs, 128 * sizeof(double)));
-    if (!s.colmax) CU_TRY(cudaMalloc(&s.colmax, 64 * sizeof(unsigned long long)));
+    if (!s.colmax) CU_TRY(cudaMalloc(&s.colmax, 65 * sizeof(unsigned long long)));
     if (!s.scratch) CU_TRY(cudaMalloc(&s.scratch, (size_t)m->sm_count * 4 * 64 * 64 * sizeof(double)));
     CU_TRY(cudaMemsetAsync(s.colmax, 0, 64 * sizeof(unsigned long long), st));
     colmax64_kernel<<<m->sm_count * 4, 256, 0, st>>>(d->X, d->n, d->ld, s.colmax);
@@ -1405,22 +1402,6 @@ static int i8_prepare(anml_model* m, const anml_design* d, cudaStream_t st) {
         if (ok && mx > 0.0) (void)std::frexp(mx, &e);  // mx = f 2^e, f in [1/2, 1)
         cs[j] = (ok && mx > 0.0) ? std::ldexp(1.0, -(e + 1)) : 1.0;
         cs[64 + j] = 1.0 / cs[j];
-        s.colmax_h[j] = mx;
-    }
-    if (meanvar && ok) {
-        auto absmax = [&](const double* v, double* out) -> int {
-            *out = 0.0;
-            if (!v) return ANML_OK;
-            double lo = 0.0, hi = 0.0;
-            int nan = 0;
-            TRY(anml_vector_minmax(m->device, v, m->n, 1, &lo, &hi, &nan));
-            if (nan || !std::isfinite(lo) || !std::isfinite(hi)) ok = false;
-            *out = std::fmax(std::fabs(lo), std::fabs(hi));
-            return ANML_OK;
-        };
-        TRY(absmax(m->obs, &s.obs_absmax));
-        TRY(absmax(m->par[0].offset, &s.off_absmax[0]));
-        TRY(absmax(m->par[1].offset, &s.off_absmax[1]));
     }
     CU_TRY(cudaMemcpyAsync(s.cs, cs, sizeof(cs), cudaMemcpyHostToDevice, st));
     CU_TRY(cudaStreamSynchronize(st));
@@ -1438,24 +1419,12 @@ static int i8_prepare(anml_model* m, const anml_design* d, cudaStream_t st) {
     }
     s.sv_scale = 1.0;
     if (ok) {
-        int e = 0;
-        const double f = std::frexp(sv_max, &e);                       // sv_max = f 2^e, f in [1/2, 1)
-        s.sv_scale = std::ldexp(1.0, f == 0.5 ? -e : -(e + 1));        // sv_max sv_scale <= 1/2
+        s.sv_scale = i8_scale_for(sv_max);  // sv_max sv_scale <= 1/2
         if (!std::isfinite(s.sv_scale) || s.sv_scale == 0.0 || !std::isfinite(1.0 / (s.sv_scale * s.sv_scale))) ok = false;
     }
     s.design = d; s.X = d->X; s.n = d->n; s.version = d->version; s.se = m->se; s.se_version = m->se_version; s.usable = ok;
-    s.obs = m->obs; s.obs_version = m->obs_version; s.off[0] = m->par[0].offset; s.off[1] = m->K > 1 ? m->par[1].offset : nullptr;
     m->all_launches += 1;
     return ANML_OK;
-}
-
-constexpr bool I8_DUAL_DEFAULT = false;
-
-// power of two s with sv_max * s <= 1/2
-static double i8_scale_for(double sv_max) {
-    int e = 0;
-    const double f = std::frexp(sv_max, &e);  // sv_max = f 2^e, f in [1/2, 1)
-    return std::ldexp(1.0, f == 0.5 ? -e : -(e + 1));
 }
 
 template <int MODE>
@@ -1474,7 +1443,7 @@ static int launch_i8_t(const anml_design* d, const FusedArgs& a, const I8Extra& 
     return ANML_OK;
 }
 
-// mode 0: one-parameter model; 3: both predictors of a mean / variance model + block (0,0); 1: term-fed block
+// mode 0: one-parameter model; 1: term-fed block (w >= 0 in a.wvec, its maximum in i8.colmax[64])
 static int run_fused_i8(anml_model* m, const anml_design* d, FusedArgs a, int mode, double sv_scale, const FinishPlan& plan, double* packed,
                         cudaStream_t st) {
     const long long nblk = (d->n + 31) / 32;
@@ -1486,11 +1455,11 @@ static int run_fused_i8(anml_model* m, const anml_design* d, FusedArgs a, int mo
     x.cs = m->i8.cs; x.scratch = m->i8.scratch;
     x.sv_scale = sv_scale;  // sqrt(w) sv_scale <= 1/2
     x.out_scale = 1.0 / (x.sv_scale * x.sv_scale);
+    x.wmax_bits = mode == 1 ? m->i8.colmax + 64 : nullptr;  // term-fed block: the kernel derives its scale from max w
     EventPair* ep = next_events(m);
     if (ep) CU_TRY(cudaEventRecord(ep->a, st));
     int rc = ANML_OK;
-    if (mode == 3) rc = launch_i8_t<3>(d, a, x, grid, st);
-    else if (mode == 1) rc = launch_i8_t<1>(d, a, x, grid, st);
+    if (mode == 1) rc = launch_i8_t<1>(d, a, x, grid, st);
     else rc = launch_i8_t<0>(d, a, x, grid, st);
     TRY(rc);
     if (ep) CU_TRY(cudaEventRecord(ep->b, st));
@@ -1499,34 +1468,6 @@ static int run_fused_i8(anml_model* m, const anml_design* d, FusedArgs a, int mo
     m->main_launches += 1;
     m->all_launches += 1;
     return launch_finish(m, grid, 4, true, d->p, plan, packed, st);
-}
-
-// Mean (identity) / variance (exp) model over one 64-column design (BASELINE config #4): H00 = U^T U with U = e^{-y1/2} X
-// and H11 = V^T V with V = sqrt(w11) X = |res| e^{-y1/2} / sqrt(2) X go to the INT8 tensor cores when sqrt(w) can be
-// bounded tightly enough in advance: |y_k| <= max|offset_k| + sum_j max_i|x_ij| |beta_kj|, |res| <= max|obs| + |y0| bound.
-// A bound costs one bit of the 48 per factor of two it overshoots; beyond 2^10 (block 00) / 2^12 (block 11) the DMMA kernels run.
-static bool i8_dual_bounds(const anml_model* m, const anml_design* d, double* scale_u, double* scale_v) {
-    if (m->no_i8 || m->no_fast || m->no_specialise || m->force_signed || m->force_generic || m->weights) return false;
-    if (!I8_DUAL_DEFAULT) {  // not yet validated on hardware in this build: opt-in
-        const char* s = getenv("ANML_B200_HESS_I8_DUAL");
-        if (!s || s[0] != '1') return false;
-    }
-    if (d->p != 64 || d->ld != 64 || !d->has3d) return false;
-    if (m->family != ANML_FAMILY_GAUSSIAN_MEANVAR || m->par[0].link != ANML_LINK_IDENTITY || m->par[1].link != ANML_LINK_EXP) return false;
-    if (const char* s = getenv("ANML_B200_HESS_I8"))
-        if (s[0] == '0') return false;
-    if (!m->i8.usable) return false;
-    double s0 = m->i8.off_absmax[0], s1 = m->i8.off_absmax[1];
-    for (int j = 0; j < 64; ++j) {
-        s0 += m->i8.colmax_h[j] * std::fabs(m->h_beta[m->par[0].off + j]);
-        s1 += m->i8.colmax_h[j] * std::fabs(m->h_beta[m->par[1].off + j]);
-    }
-    const double hmax = std::exp(0.5 * s1);
-    const double sv_u = hmax, sv_v = (m->i8.obs_absmax + s0) * hmax * 0.70710678118654757;
-    if (!(sv_u <= 1024.0) || !(sv_v <= 4096.0) || !(sv_v > 0.0)) return false;
-    *scale_u = i8_scale_for(sv_u);
-    *scale_v = i8_scale_for(sv_v);
-    return true;
 }
 
 // Gaussian prior terms as a separate launch: only the paths whose epilogue is not the fused one
@@ -1876,37 +1817,6 @@ static int eval_general(anml_model* m, int want, double* packed, cudaStream_t st
     if (dual) {
         const anml_design* d = m->par[0].design;
         const int off0 = m->par[0].off, off1 = m->par[1].off;
-        double scale_u = 1.0, scale_v = 1.0;
-        bool i8 = false;
-        if (hess && !m->no_specialise && !m->no_i8 && m->family == ANML_FAMILY_GAUSSIAN_MEANVAR && d->p == 64 && d->ld == 64 && d->has3d) {
-            TRY(i8_prepare(m, d, st));
-            i8 = i8_dual_bounds(m, d, &scale_u, &scale_v);
-        }
-        if (i8) {
-            // blocks (0,0) and (1,1) on the INT8 tensor cores, the signed cross block (0,1) on DMMA
-            FusedArgs a;
-            memset(&a, 0, sizeof(a));
-            a.n = m->n; a.p = d->p; a.link = m->par[0].link; a.link1 = m->par[1].link; a.family = m->family; a.fast = 1;
-            a.beta = m->d_beta + m->par[0].pad_off; a.beta1 = m->d_beta + m->par[1].pad_off;
-            a.obs = m->obs; a.offset = m->par[0].offset; a.offset1 = m->par[1].offset;
-            a.out_r1 = m->vec[3]; a.out_w01 = m->vec[5]; a.out_w11 = m->vec[6];  // vec[6] receives sqrt(w11) here
-            FinishPlan p0;
-            p0.row_off = off0; p0.col_off = off0; p0.prior_k = 0; p0.prior_obj = true;
-            TRY(run_fused_i8(m, d, a, 3, scale_u, p0, packed, st));
-            FusedArgs b;
-            memset(&b, 0, sizeof(b));
-            b.n = m->n; b.p = d->p; b.rvec = m->vec[3]; b.wvec = m->vec[6];
-            FinishPlan p1;
-            p1.row_off = off1; p1.col_off = off1; p1.prior_k = 1; p1.obj_mode = 0;
-            TRY(run_fused_i8(m, d, b, 1, scale_v, p1, packed, st));
-            FusedArgs c;
-            memset(&c, 0, sizeof(c));
-            c.n = m->n; c.p = d->p; c.rvec = nullptr; c.wvec = m->vec[5];
-            FinishPlan px;
-            px.row_off = off0; px.col_off = off1; px.write_grad = false; px.obj_mode = 0; px.write_flag = true;
-            TRY(run_fused_block(m, d, c, true, 1, px, packed, true, st));
-            return ANML_OK;
-        }
         if (hess && !m->no_specialise) {
             FusedArgs a;
             memset(&a, 0, sizeof(a));
@@ -1917,6 +1827,36 @@ static int eval_general(anml_model* m, int want, double* packed, cudaStream_t st
             FinishPlan p0;
             p0.row_off = off0; p0.col_off = off0; p0.prior_k = 0; p0.prior_obj = true;
             TRY(run_fused_block(m, d, a, true, 3, p0, packed, true, st));
+            // Block (1,1) = X^T diag(w11) X, w11 = res^2 / (2 v) >= 0 for the identity / exp pair: on the INT8 tensor cores
+            // (fused_hess_i8.cuh MODE 1).  Its digit scale needs max w11, which the launch above has just left in vec[6]:
+            // one 0.8 GB read, and the kernel takes the scale from device memory.  Block (0,0) stays on DMMA: sqrt(w00) =
+            // e^{-y1/2} has no bound that is known before the pass that computes it, and a loose a-priori bound costs
+            // precision quadratically (profiles/r2_ab_i8.txt).
+            const bool i8 = !m->no_i8 && !m->no_fast && !m->force_signed && !m->weights && d->p == 64 && d->ld == 64 && d->has3d &&
+                            m->par[0].link == ANML_LINK_IDENTITY && m->par[1].link == ANML_LINK_EXP &&
+                            !(getenv("ANML_B200_HESS_I8") && getenv("ANML_B200_HESS_I8")[0] == '0');
+            if (i8) {
+                TRY(i8_prepare(m, d, st));
+                if (m->i8.usable) {
+                    CU_TRY(cudaMemsetAsync(m->i8.colmax + 64, 0, sizeof(unsigned long long), st));
+                    wmax_kernel<<<m->sm_count * 8, 256, 0, st>>>(m->vec[6], m->n, m->i8.colmax + 64);
+                    CU_TRY(cudaGetLastError());
+                    m->all_launches += 1;
+                    FusedArgs b;
+                    memset(&b, 0, sizeof(b));
+                    b.n = m->n; b.p = d->p; b.rvec = m->vec[3]; b.wvec = m->vec[6];
+                    FinishPlan p1;
+                    p1.row_off = off1; p1.col_off = off1; p1.prior_k = 1; p1.obj_mode = 0;
+                    TRY(run_fused_i8(m, d, b, 1, 1.0, p1, packed, st));
+                    FusedArgs c;
+                    memset(&c, 0, sizeof(c));
+                    c.n = m->n; c.p = d->p; c.rvec = nullptr; c.wvec = m->vec[5];
+                    FinishPlan px;
+                    px.row_off = off0; px.col_off = off1; px.write_grad = false; px.obj_mode = 0; px.write_flag = true;
+                    TRY(run_fused_block(m, d, c, true, 1, px, packed, true, st));
+                    return ANML_OK;
+                }
+            }
         } else {
             TRY(run_dual_terms(m, packed, st));  // objective + (r0, r1, w00, w01, w11)
             FusedArgs a;

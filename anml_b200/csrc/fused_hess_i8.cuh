@@ -40,6 +40,8 @@ struct I8Extra {
     const double* cs;       // [64] column scales (powers of two), then [64] their reciprocals
     double sv_scale;        // power of two folded into sqrt(w) (1 for the logistic w <= 1/4)
     double out_scale;       // 1 / sv_scale^2
+    const unsigned long long* wmax_bits;  // MODE 1: bit pattern of max_i w_i (device, written by an earlier launch); the kernel
+                                          // derives sv_scale from it instead of taking the host's
     double* scratch;        // [gridDim.x][2][2][64][64] FP64 flush target
 };
 
@@ -64,7 +66,7 @@ struct I8Cfg {
     static constexpr int TR_BYTES = 4 * 36 * 8;                // per helper: transpose scratch
     static constexpr int HT_BYTES = 256;                       // per helper: r and sqrt(w) of its 16 rows
     static constexpr int HREC_BYTES = (NB8 + 1) * 256;         // per helper: gradient / objective record at the end (in the idle ring)
-    static constexpr int SMEM_BYTES = 1024 + NBUF * BUF_BYTES + 512 /*barriers, TMEM slot*/ + 3 * 64 * 8 /*beta, column scales, beta1*/ + NHELP * (TR_BYTES + HT_BYTES);
+    static constexpr int SMEM_BYTES = 1024 + NBUF * BUF_BYTES + 512 /*barriers, TMEM slot*/ + 2 * 64 * 8 /*beta, column scales*/ + NHELP * (TR_BYTES + HT_BYTES);
     static_assert(NHELP * HREC_BYTES <= NBUF * BUF_BYTES, "the helper records reuse the ring");
 };
 
@@ -111,10 +113,9 @@ constexpr double I8_MAGIC = 16.0 + (double)0x808080808080ull / 281474976710656.0
 //      (m, n) carries weight 2^-8(2 (pp + pp') + 2 + x_m + x_n);
 //   4. the MMAs' commit frees the buffer for the next TMA.
 // MODE 0: row terms of a one-parameter model taken here (binomial/expit, gaussian/identity);
-// MODE 3: two parameters over this one design, mean identity / variance exp (BASELINE config #4): both linear predictors,
-//         the row terms of the pair, objective, g0 and H00 = U^T U with U = sqrt(w00) X = e^{-y1/2} X; writes r1, w01 and
-//         sqrt(w11) to a.out_r1 / out_w01 / out_w11 for the launches that follow;
-// MODE 1: term-fed block: r from a.rvec (nullptr: no gradient), sqrt(w) >= 0 from a.wvec; no y pass, no row terms.
+// MODE 1: term-fed block (BASELINE config #4, block (1,1)): r from a.rvec (nullptr: no gradient), w >= 0 from a.wvec, sqrt taken
+//         here; no y pass, no row terms.  The bound on sqrt(w) is the exact maximum of the vector, left in device memory by
+//         wmax_kernel: the scale is derived on the device, so it is as tight as for the logistic model.
 template <int MODE>
 __global__ void __launch_bounds__(I8Cfg::THREADS, 1) fused_hess_i8_kernel(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const I8Extra x) {
     using C = I8Cfg;
@@ -129,8 +130,7 @@ __global__ void __launch_bounds__(I8Cfg::THREADS, 1) fused_hess_i8_kernel(const 
     const uint32_t slot_u32 = done_u32 + 8;                        // TMEM base address
     const uint32_t beta_u32 = full_u32 + 512;
     const uint32_t cs_u32 = beta_u32 + 64 * 8;
-    const uint32_t beta1_u32 = cs_u32 + 64 * 8;
-    const uint32_t tr_base = beta1_u32 + 64 * 8;
+    const uint32_t tr_base = cs_u32 + 64 * 8;
     const uint32_t hterm_base = tr_base + NHELP * C::TR_BYTES;
     const uint32_t hrec_base = smem_base;  // after the last epoch the ring is idle
     static_assert((3 * NBUF + 1) * 8 + 16 <= 512, "barrier area");
@@ -148,10 +148,17 @@ __global__ void __launch_bounds__(I8Cfg::THREADS, 1) fused_hess_i8_kernel(const 
         mbar_init(done_u32, 1);
         mbar_fence_init();
     }
+    double sv_scale = x.sv_scale, out_scale = x.out_scale;
+    if (MODE == 1 && x.wmax_bits) {
+        // sqrt(w) <= sqrt(wmax) = f 2^e, f in [1/2, 1): sv_scale = 2^-(e+1) keeps sqrt(w) sv_scale < 1/2
+        const double svm = sqrt(__longlong_as_double((long long)*x.wmax_bits));
+        const int e = ((__double2hiint(svm) >> 20) & 0x7ff) - 1022;
+        sv_scale = svm > 0.0 ? __longlong_as_double((long long)(1023 - (e + 1)) << 52) : 1.0;
+        out_scale = 1.0 / (sv_scale * sv_scale);
+    }
     if (threadIdx.x < 64) {
         sts64(beta_u32 + threadIdx.x * 8, MODE == 1 ? 0.0 : a.beta[threadIdx.x]);
-        sts64(beta1_u32 + threadIdx.x * 8, MODE == 3 ? a.beta1[threadIdx.x] : 0.0);
-        sts64(cs_u32 + threadIdx.x * 8, x.cs[threadIdx.x] * x.sv_scale);  // the global factor of sqrt(w) rides on the column scale
+        sts64(cs_u32 + threadIdx.x * 8, x.cs[threadIdx.x] * sv_scale);  // the global factor of sqrt(w) rides on the column scale
     }
     if (warp == NHELP) {
         __syncwarp();
@@ -180,7 +187,7 @@ __global__ void __launch_bounds__(I8Cfg::THREADS, 1) fused_hess_i8_kernel(const 
         uint32_t bad_range = 0;
         const uint32_t tr_u32 = tr_base + warp * C::TR_BYTES;
         const uint32_t ht_u32 = hterm_base + warp * C::HT_BYTES;
-        const double sv_max = 0.5 / x.sv_scale;
+        const double sv_max = 0.5 / sv_scale;
         const int rl = lane & 15;                 // position 4s' + t' of the row whose terms this lane evaluates (lanes 16..31 mirror 0..15)
         const int my_row = 16 * h + 2 * (rl & 3) + ((rl >> 2) & 1) + 8 * (rl >> 3);
         // reading: k-step s holds rows 16h + 2t + (s & 1) + 8 (s >> 1) of column group j, 16-byte chunk g ^ (row & 7)
@@ -205,74 +212,53 @@ __global__ void __launch_bounds__(I8Cfg::THREADS, 1) fused_hess_i8_kernel(const 
                 const bool valid = row < a.n;
                 double rr = 0.0, sc = 0.0;
                 if (MODE == 1) {
-                    // ---- term-fed: r and sqrt(w) of the row come from the vectors of an earlier launch
+                    // ---- term-fed: r and w of the row come from the vectors of an earlier launch
                     if (valid) {
                         if (a.rvec) rr = a.rvec[row];
-                        sc = a.wvec[row];
-                        if (!(sc <= sv_max)) bad_range = 0xffff0000u;
+                        sc = sqrt(a.wvec[row]);
+                        if (!(sc <= sv_max)) bad_range = 0xffff0000u;  // (also catches w < 0: NaN)
                     }
                     mbar_wait(full_u32 + buf * 8, (uint32_t)((q / NBUF) & 1));
                 } else {
-                    double off = 0.0, off1 = 0.0, ob = 0.0, se = 1.0;
+                    double off = 0.0, ob = 0.0, se = 1.0;
                     if (valid) {
                         if (a.offset) off = a.offset[row];
                         ob = a.obs[row];
-                        if (MODE == 0 && a.se) se = a.se[row];
-                        if (MODE == 3 && a.offset1) off1 = a.offset1[row];
+                        if (a.se) se = a.se[row];
                     }
                     mbar_wait(full_u32 + buf * 8, (uint32_t)((q / NBUF) & 1));
-                    // ---- pass 1: linear predictor(s) of this warp's 16 rows
-                    double part[4] = {0.0, 0.0, 0.0, 0.0}, part1[4] = {0.0, 0.0, 0.0, 0.0};
+                    // ---- pass 1: linear predictor of this warp's 16 rows
+                    double part[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const double2 b = lds128(beta_u32 + (16 * j + 2 * g) * 8);
-                        const double2 b1 = MODE == 3 ? lds128(beta1_u32 + (16 * j + 2 * g) * 8) : make_double2(0.0, 0.0);
 #pragma unroll
                         for (int s = 0; s < 4; ++s) {
                             const double2 v = lds128(bp + j * 4096 + rd_off[s]);
                             part[s] = fma(v.y, b.y, fma(v.x, b.x, part[s]));
-                            if (MODE == 3) part1[s] = fma(v.y, b1.y, fma(v.x, b1.x, part1[s]));
                         }
                     }
                     // lane (g,t) stores part[s] at [s][g][t]; the lane at position 4s' + t' adds the 8 entries [s'][*][t']
-                    auto transpose_sum = [&](const double (&pt)[4]) {
 #pragma unroll
-                        for (int s = 0; s < 4; ++s) sts64(tr_u32 + (s * 36 + lane) * 8, pt[s]);
-                        __syncwarp();
+                    for (int s = 0; s < 4; ++s) sts64(tr_u32 + (s * 36 + lane) * 8, part[s]);
+                    __syncwarp();
+                    double y;
+                    {
                         const uint32_t base = tr_u32 + ((rl >> 2) * 36 + (rl & 3)) * 8;
                         const double q0 = lds64(base), q1 = lds64(base + 32), q2 = lds64(base + 64), q3 = lds64(base + 96);
                         const double q4 = lds64(base + 128), q5 = lds64(base + 160), q6 = lds64(base + 192), q7 = lds64(base + 224);
-                        __syncwarp();
-                        return ((q0 + q1) + (q2 + q3)) + ((q4 + q5) + (q6 + q7));
-                    };
-                    const double y = transpose_sum(part);
-                    if (MODE == 0) {
-                        if (valid) {
-                            const RowTerms1 rt = row_terms1<true, true>(a.family, a.link, true, y + off, ob, se);
-                            bad_domain |= !rt.ok;
-                            if (lane < 16) {
-                                objacc += rt.l;
-                                logprod.mul(rt.ls);
-                            }
-                            rr = rt.r;
-                            sc = rt.sw;
-                            if (!(sc <= sv_max)) bad_range = 0xffff0000u;  // outside the digit range: flagged, the host reports it
+                        y = ((q0 + q1) + (q2 + q3)) + ((q4 + q5) + (q6 + q7));
+                    }
+                    if (valid) {
+                        const RowTerms1 rt = row_terms1<true, true>(a.family, a.link, true, y + off, ob, se);
+                        bad_domain |= !rt.ok;
+                        if (lane < 16) {
+                            objacc += rt.l;
+                            logprod.mul(rt.ls);
                         }
-                    } else {
-                        const double y1 = transpose_sum(part1);
-                        if (valid) {
-                            const RowTerms2 rt = row_terms2(a.link, a.link1, y + off, y1 + off1, ob, true);
-                            bad_domain |= !rt.ok;
-                            if (lane < 16) {
-                                objacc += rt.l;
-                                a.out_r1[row] = rt.r1;
-                                a.out_w01[row] = rt.w01;
-                                a.out_w11[row] = sqrt(rt.w11);  // sqrt(w11) = |res| e^{-y1/2} / sqrt(2): what the MODE 1 launch of block (1,1) reads
-                            }
-                            rr = rt.r0;
-                            sc = rt.sw00;
-                            if (!(sc >= 0.0 && sc <= sv_max) || !(rt.w11 >= 0.0)) bad_range = 0xffff0000u;
-                        }
+                        rr = rt.r;
+                        sc = rt.sw;
+                        if (!(sc <= sv_max)) bad_range = 0xffff0000u;  // outside the digit range: flagged, the host reports it
                     }
                 }
                 if (lane < 16) {
@@ -471,7 +457,7 @@ __global__ void __launch_bounds__(I8Cfg::THREADS, 1) fused_hess_i8_kernel(const 
             if (nq > 0) {
                 const double* T = scr + 2 * 64 * 64;
                 const size_t ij = (size_t)c1 * 64 + c2, ji = (size_t)c2 * 64 + c1;
-                s = ((scr[ij] + scr[4096 + ij]) + ((T[ij] + T[4096 + ij]) + (T[ji] + T[4096 + ji]))) * (ics[c1] * ics[c2] * x.out_scale);
+                s = ((scr[ij] + scr[4096 + ij]) + ((T[ij] + T[4096 + ij]) + (T[ji] + T[4096 + ji]))) * (ics[c1] * ics[c2] * out_scale);
             }
         } else {
             const int l = e - 2 * NT * 32;
@@ -483,6 +469,22 @@ __global__ void __launch_bounds__(I8Cfg::THREADS, 1) fused_hess_i8_kernel(const 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == NHELP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+// largest entry of a non-negative vector, as a bit pattern (0 for an empty / all-zero vector; NaN or negative entries give a
+// pattern above every finite positive double, which the consumer's range check then rejects)
+__global__ void wmax_kernel(const double* __restrict__ w, long long n, unsigned long long* __restrict__ out) {
+    unsigned long long m = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(w[i]);
+        m = b > m ? b : m;
+    }
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(FULL_MASK, m, k);
+        m = o > m ? o : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
 
 // largest |x| per column (64 columns), as the bit pattern of a non-negative double (integer order = value order)

@@ -465,37 +465,32 @@ def meanvar64_model(n, seed, scale=1.0, offsets=False):
     return model, x, want, (d, bufs)
 
 
-def _dual_i8_enabled():
-    import os
-
-    from anml_b200 import _native as N
-
-    return os.environ.get("ANML_B200_HESS_I8_DUAL") == "1" or N.load().anml_version() >= 201
-
-
 @pytest.mark.parametrize("n,offsets", [(1, False), (33, False), (5000, True), (200_003, False)])
 def test_i8_mean_variance_blocks(n, offsets):
-    if not _dual_i8_enabled():
-        pytest.skip("INT8 blocks of the mean / variance model are opt-in in this build (ANML_B200_HESS_I8_DUAL=1)")
-    # BASELINE config #4 shape: blocks (0,0) and (1,1) on the INT8 tensor cores, the signed cross block on DMMA
+    # BASELINE config #4 shape: block (1,1) (w11 >= 0, bound = its exact maximum) on the INT8 tensor cores, blocks (0,0) and
+    # the signed cross block (0,1) on DMMA
     model, x, want, keep = meanvar64_model(n, seed=n + 3, offsets=offsets)
     got = model.eval(x)
     ks = model.last_kernels()
-    assert [k.split("<")[0] for k in ks] == ["fused_hess_i8_kernel", "fused_hess_i8_kernel", "fused_hess_kernel"], ks
+    assert [k.split("<")[0] for k in ks] == ["fused_hess_kernel", "fused_hess_i8_kernel", "fused_hess_kernel"], ks
     check(got, want)
     again = model.eval(x)
     assert got[0] == again[0] and np.array_equal(got[1], again[1]) and np.array_equal(got[2], again[2])
     model.set_option("hess_i8", 0)
     ref = model.eval(x)
     assert all(k.startswith("fused_hess_kernel") for k in model.last_kernels())
-    assert np.abs(got[2] - ref[2]).max() <= 1e-11 * np.abs(ref[2]).max()
+    assert np.abs(got[2] - ref[2]).max() <= 1e-12 * np.abs(ref[2]).max()
     assert np.abs(got[1] - ref[1]).max() <= 1e-12 * np.abs(ref[1]).max()
     assert abs(got[0] - ref[0]) <= 1e-12 * abs(ref[0])
 
 
-def test_i8_mean_variance_falls_back_when_the_weight_bound_is_loose():
-    # variance coefficients 40 times larger: the a-priori bound on e^{-y1/2} exceeds 2^10, the DMMA kernels run
-    model, x, want, keep = meanvar64_model(4000, seed=12, scale=40.0)
+def test_i8_mean_variance_wide_range_of_weights():
+    # variance coefficients 8 times larger: w11 = res^2 / (2 v) spans many decades; the digit scale follows its exact maximum
+    model, x, want, keep = meanvar64_model(30011, seed=12, scale=8.0)
     got = model.eval(x)
-    assert all(k.startswith("fused_hess_kernel") for k in model.last_kernels()), model.last_kernels()
-    check(got, want, og=1e-9, h=1e-9)
+    assert "fused_hess_i8_kernel<1>" in model.last_kernels(), model.last_kernels()
+    check(got, want)
+    model.set_option("hess_i8", 0)
+    ref = model.eval(x)
+    d = np.sqrt(np.abs(np.diag(ref[2])))
+    assert np.abs((got[2] - ref[2]) / np.outer(d, d)).max() <= 1e-10
