@@ -33,7 +33,7 @@ def demangle(n):
     return subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip().replace("anml::", "")
 
 
-WANT = ["fused_hess_i8_kernel", "fused_hess_kernel<4, 2, false, 0, true, 32>", "fused_hess_kernel<4, 2, true, 3, true, 32>", "fused_hess_kernel<4, 2, true, 1, true, 32>",
+WANT = ["fused_hess_i8_kernel<0>", "fused_hess_i8_kernel<1>", "fused_hess_kernel<4, 2, false, 0, true, 32>", "fused_hess_kernel<4, 2, true, 3, true, 32>", "fused_hess_kernel<4, 2, true, 1, true, 32>",
         "fused_hess_kernel<1, 4, false, 0, true, 64>", "fused_eval_kernel<4, false, 0>", "wide_hessian_kernel", "spline_banded_bulk_kernel<3, true, false>", "spline_banded_eval_kernel<3, true, false>",
         "spline_design_kernel<3>", "finish_fused_kernel", "banded_finish_kernel", "comm_allreduce_kernel"]
 print("# SASS opcode counts per kernel (static instructions; `cuobjdump -sass` of the shipped library)\n")
