@@ -42,3 +42,21 @@ def test_gram_matrix_error_bound():
     bound = n * (2 * 2.0**-49 * 0.25 + 2.0**-49 * 2.0**-49 + 12 * 2.0**-50)
     assert np.abs(H - want).max() <= bound
     assert np.abs(H - want).max() <= 1e-12 * np.abs(want).max()
+
+
+def test_precision_falls_quadratically_with_a_loose_scale():
+    """Why the digit scale must follow the data tightly (block (0,0) of the mean / variance model stays on
+    DMMA, block (1,1) takes its scale from the exact max w): values that sit 2^-k below the scale lose 2^2k of relative
+    accuracy, because the dropped digit-plane products assume a leading digit in plane 1."""
+    rng = np.random.default_rng(3)
+    n, p = 64, 4
+    X = rng.uniform(-0.25, 0.25, size=(n, p))
+    rel = []
+    for k in (0, 5, 10):
+        Xt = X * 2.0**-k
+        H = S.gram(Xt)
+        want = Xt.T @ Xt
+        rel.append(np.abs(H - want).max() / np.abs(want).max())
+    assert rel[0] <= 1e-13                              # 5e-15 measured
+    assert 1e-13 < rel[1] <= 1e-10                      # 7e-12: ~2^10 worse
+    assert rel[2] > 100 * rel[1] and rel[2] > 1e-9      # 5e-9: ~2^20 worse, outside BASELINE's Hessian tolerance
