@@ -131,6 +131,7 @@ struct anml_model {
     bool force_signed = false;
     unsigned long long se_version = 0;  // bumped by anml_model_set_obs_se
     std::string last_kernels;           // timed kernels of the last evaluation, ';'-separated
+    bool i8_force = false;  // option "hess_i8" = 2: also below I8_MIN_ROWS (tests)
     bool no_i8 = false;  // option "hess_i8" = 0: keep the Hessian of 64-column logistic / Gaussian models on DMMA
     // INT8-tensor-core Hessian (fused_hess_i8.cuh): column scales of the design they were taken from, flush scratch
     struct I8State {
@@ -1064,7 +1065,10 @@ extern "C" int anml_model_set_option(anml_model* m, const char* name, int64_t va
     else if (!strcmp(name, "no_warp_specialisation")) m->no_specialise = value != 0;
     else if (!strcmp(name, "force_signed_weights")) m->force_signed = value != 0;
     else if (!strcmp(name, "banded_register_prefetch")) m->banded_registers = value != 0;
-    else if (!strcmp(name, "hess_i8")) m->no_i8 = value == 0;
+    else if (!strcmp(name, "hess_i8")) {
+        m->no_i8 = value == 0;
+        m->i8_force = value == 2;
+    }
     else if (!strcmp(name, "hess_i8_rescan")) m->i8.design = nullptr;
     else return fail(ANML_EINVAL, "unknown option '%s'", name);
     return ANML_OK;
@@ -1360,7 +1364,15 @@ static int run_fused_block(anml_model* m, const anml_design* d, FusedArgs a, boo
 // ---- Hessian on the INT8 tensor cores (fused_hess_i8.cuh) -------------------------------------------------
 // One-parameter models whose sqrt(w) has a bound known in advance: canonical logistic (w <= 1/4) and the
 // Gaussian identity model (w = 1 / obs_se^2 <= 1 / min(obs_se)^2).  64 columns, dense row pitch, no per-row weights.
+// Below this many rows per device the DMMA kernels run: the digit planes bound the ABSOLUTE error of every row's
+// contribution (2^-47 of the square of the column's largest scaled value); over many rows these errors average out (1e-14 at
+// the sizes this path is for), a few hundred rows of a heavy-tailed column do not give them the chance
+// (tests/test_i8_split_cpu.py::test_precision_falls_quadratically_with_a_loose_scale), and a persistent kernel with a
+// TMEM flush buys nothing at that size anyway.
+constexpr long long I8_MIN_ROWS = 8192;
+
 static bool i8_eligible(const anml_model* m, const anml_design* d, bool hess) {
+    if (m->n < I8_MIN_ROWS && !m->i8_force) return false;
     if (!hess || m->no_i8 || m->no_fast || m->no_specialise || m->force_signed || m->force_generic) return false;
     if (m->K != 1 || d->p != 64 || d->ld != 64 || !d->has3d || m->weights) return false;
     if (const char* s = getenv("ANML_B200_HESS_I8"))
@@ -1832,7 +1844,8 @@ static int eval_general(anml_model* m, int want, double* packed, cudaStream_t st
             // one 0.8 GB read, and the kernel takes the scale from device memory.  Block (0,0) stays on DMMA: sqrt(w00) =
             // e^{-y1/2} has no bound that is known before the pass that computes it, and a loose a-priori bound costs
             // precision quadratically (profiles/r2_ab_i8.txt).
-            const bool i8 = !m->no_i8 && !m->no_fast && !m->force_signed && !m->weights && d->p == 64 && d->ld == 64 && d->has3d &&
+            const bool i8 = !m->no_i8 && (m->n >= I8_MIN_ROWS || m->i8_force) && !m->no_fast && !m->force_signed && !m->weights && d->p == 64 &&
+                            d->ld == 64 && d->has3d &&
                             m->par[0].link == ANML_LINK_IDENTITY && m->par[1].link == ANML_LINK_EXP &&
                             !(getenv("ANML_B200_HESS_I8") && getenv("ANML_B200_HESS_I8")[0] == '0');
             if (i8) {

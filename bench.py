@@ -620,7 +620,7 @@ def run_gpu(args, cfg):
     P = 2 * p if kind == "meanvar" else p
 
     # ---- parity check of the sharded path on a small problem (every rank takes part) ----
-    n_small = 30_011
+    n_small = 70_001  # (at least 8192 rows per rank at N = 8: the INT8 Hessian path takes part in the check)
     small_cfg = dict(cfg, n=n_small)
     slo, shi = shard_rows(n_small, world, rank)
     sdata = make_shard(torch, dev, small_cfg, slo, shi, seed_shift=777)

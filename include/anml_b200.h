@@ -174,10 +174,10 @@ int anml_model_main_kernel(const anml_model* m, char* out, int out_len);
 /* the timed kernels of the last evaluation in launch order, ';'-separated (a mean / variance model launches three) */
 int anml_model_last_kernels(const anml_model* m, char* out, int out_len);
 /* Evaluation switches (all default 0 unless noted; development / A-B use, results stay within tolerance either way):
- *   "hess_i8" (default 1)       Hessian of an eligible model (one parameter, exactly 64 dense columns, binomial/expit or
+ *   "hess_i8" (default 1)       Hessian of an eligible model (at least 8192 rows on the device, one parameter, exactly 64 dense columns, binomial/expit or
  *                               gaussian/identity, no per-row weights) on the INT8 tensor cores
  *                               (csrc/fused_hess_i8.cuh), and block (1,1) of a mean (identity) / variance (exp) model over one
- *                               64-column design; 0 keeps them on the FP64 tensor cores (DMMA).  Environment
+ *                               64-column design; 0 keeps them on the FP64 tensor cores (DMMA), 2 lifts the row minimum.  Environment
  *                               ANML_B200_HESS_I8=0 switches it off for the whole process.
  *   "hess_i8_rescan"            forget the per-column value ranges the INT8 path recorded for the design (taken again at
  *                               the next evaluation); needed only after rewriting a WRAPPED device matrix in place --

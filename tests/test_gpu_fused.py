@@ -330,6 +330,7 @@ def i8_model(family, n, seed, scale_cols=False, offset=False, prior=True):
     if prior:
         pr = {"direct": (np.zeros(64), np.full(64, 2.0))}
         model.set_gaussian_prior(0, *pr["direct"])
+    model.set_option("hess_i8", 2)  # also below the 8192-row minimum of the default
     return model, (X, obs, off, link, x, pr), (design, off_buf)
 
 
@@ -429,6 +430,22 @@ def test_i8_hessian_gaussian_with_obs_se():
     check(got2, O.model_eval_fused("gaussian", obs, [X], [link], x, obs_se=se2))
 
 
+def test_i8_default_row_minimum():
+    # by default small problems stay on DMMA (the digit planes bound absolute, not relative, row errors: DESIGN.md 3.1a)
+    from anml_b200 import _native as N
+
+    for n, want_i8 in ((8191, False), (8192, True)):
+        X, obs, se, off, link, x = make_problem("binomial", n, 64, 5)
+        design = N.Design(n, 64)
+        design.set_columns(0, X)
+        model = N.NativeModel(n, "binomial", 1)
+        model.set_param(0, design, N.LINK_CODES["Expit"])
+        model.set_obs(obs)
+        got = model.eval(x)
+        assert model.main_kernel().startswith("fused_hess_i8_kernel") == want_i8, (n, model.main_kernel())
+        check(got, O.model_eval_fused("binomial", obs, [X], [link], x))
+
+
 def test_i8_not_used_outside_its_domain():
     # per-row weights, Poisson, p != 64: the DMMA kernel
     from anml_b200 import _native as N
@@ -459,6 +476,7 @@ def meanvar64_model(n, seed, scale=1.0, offsets=False):
     model.set_param(1, d, N.LINK_CODES["Exp"], bufs[1])
     model.set_obs(obs)
     model.set_gaussian_prior(0, np.zeros(64), np.full(64, 3.0))
+    model.set_option("hess_i8", 2)
     x = np.concatenate([0.6 * b0, 0.6 * b1])
     pri = [{"direct": (np.zeros(64), np.full(64, 3.0))}, None]
     want = O.model_eval_fused("gaussian_meanvar", obs, [X, X], ["identity", "exp"], x, offsets=off if offsets else None, priors=pri)
