@@ -170,3 +170,35 @@ def test_two_rank_gloo_spline_knots_are_those_of_the_whole_data_set():
     for p in procs:
         p.join(timeout=60)
     assert all(r[0] == "ok" for r in results), results
+
+
+def test_range_flag_of_the_int8_hessian_path_is_reported_and_triggers_a_rescan():
+    """Flag values >= 1024 in the packed record come from csrc/fused_hess_i8.cuh (a value outside the recorded column
+    ranges); the sharded model turns them into an error -- never a silently wrong Hessian -- and asks the local
+    evaluator to take the ranges again.  Smaller non-zero flags stay the Log/Logit domain error."""
+    import torch
+
+    P = 3
+
+    class FlagShard:
+        def __init__(self, flag):
+            self.num_coefs, self.packed_size, self.flag, self.rescans = P, 2 + P + P * P, flag, 0
+
+        def eval_packed(self, x, want_hessian):
+            rec = torch.zeros(self.packed_size, dtype=torch.float64)
+            rec[0] = 1.0
+            rec[-1] = self.flag
+            return rec
+
+        def rescan_ranges(self):
+            self.rescans += 1
+
+    ok = FlagShard(0.0)
+    obj, grad, hess = ShardedModel(ok).evaluate(np.zeros(P), True)
+    assert obj == 1.0 and hess.shape == (P, P) and ok.rescans == 0
+    ranged = FlagShard(1024.0)
+    with pytest.raises(RuntimeError, match="INT8 Hessian path"):
+        ShardedModel(ranged).evaluate(np.zeros(P), True)
+    assert ranged.rescans == 1
+    with pytest.raises(ValueError, match="domain"):
+        ShardedModel(FlagShard(1.0)).evaluate(np.zeros(P), True)
