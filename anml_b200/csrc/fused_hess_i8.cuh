@@ -108,9 +108,10 @@ constexpr double I8_MAGIC = 16.0 + (double)0x808080808080ull / 281474976710656.0
 //      of group j hold, for k = 2 x + ch (x = plane parity inside a plane pair, ch = which 8 of the 16 columns) and plane
 //      pair pp = 0..2, a core-matrix pair at j 4096 + k 1024 + pp 288 (+144 for rows 16..31, the second K half);
 //   3. seen through a descriptor with SBO = 1024 the buffer is, for every plane pair, a K-major 128 x 32 int8 operand
-//      whose row m = 32 j + 16 x + 8 ch + r is digit plane 2 pp + 1 + x of column 16 j + 8 ch + r; six MMAs
-//      (M = N = 128) form pair(pp) x pair(pp') for pp + pp' <= 2 into TMEM block pp + pp' (128 columns), where entry
-//      (m, n) carries weight 2^-8(2 (pp + pp') + 2 + x_m + x_n);
+//      whose row m = 32 j + 16 x + 8 ch + r is digit plane 2 pp + 1 + x of column 16 j + 8 ch + r; four MMAs
+//      (M = N = 128) form pair(pp) x pair(pp') for (pp, pp') = (0,0), (0,1), (0,2), (1,1) into four 128-column TMEM
+//      blocks, where entry (m, n) carries weight 2^-8(2 (pp + pp') + 2 + x_m + x_n); (1,0) and (2,0) are the
+//      transposes of (0,1) and (0,2) and are added when the record is written;
 //   4. the MMAs' commit frees the buffer for the next TMA.
 // MODE 0: row terms of a one-parameter model taken here (binomial/expit, gaussian/identity);
 // MODE 1: term-fed block (BASELINE config #4, block (1,1)): r from a.rvec (nullptr: no gradient), w >= 0 from a.wvec, sqrt taken
